@@ -1,0 +1,678 @@
+// kassign_kernels.cuh — hand-written sm_100a kernels for the kafka-assigner hot path.
+//
+// Reference being replaced (KAS = KafkaAssignmentStrategy.java, KTA = KafkaTopicAssigner.java):
+//   kernel A  ka_sticky_spread_kernel   KTA:49-69 (RF inference/validation), KAS:65-71 (capacity),
+//                                       KAS:73-99 (node/rack table), KAS:101-131 (sticky fill),
+//                                       KAS:133-160 (orphans), KAS:162-200 (rotated first-fit spread)
+//   kernels T ka_ticket_*               no reference counterpart: they number, per broker, the partitions
+//                                       that contain it in global (topic, partition) order so that the
+//                                       serial chain of KAS:202-239 can run as an exact dataflow
+//   kernel B  ka_leader_order_kernel    KAS:202-239 + PreferenceListOrderTracker KAS:244-302 against the
+//                                       cross-topic Context.counter (KAS:360-369, KTA:19-23)
+//
+// Everything is integer indexing: no tensor cores. Broker table staged into shared memory with one TMA
+// bulk copy per CTA (cp.async.bulk + mbarrier), per-topic state (broker loads, replica slab) lives in
+// shared memory, decisions that depend on visit order are taken with warp ballots / match / shuffles in
+// the reference's order — never by an atomics race.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define KA_MAX_SLOTS 8      // max replicas per partition row (out_stride)
+#define KA_DEAD 0xFFFFu     // "broker not in the live set" marker in 16-bit index space
+#define KA_FULL 0xFFFFFFFFu
+
+// Error codes (mirror include/kassign.h)
+#define KA_E_RF_MISMATCH 1
+#define KA_E_RF_NOT_POSITIVE 2
+#define KA_E_RF_GT_BROKERS 3
+#define KA_E_UNASSIGNABLE 4
+#define KA_E_HASH_INDEX 5
+#define KA_E_INTERNAL_SPIN -5
+
+enum { KA_LUT_SMEM = 0, KA_LUT_GLOBAL = 1, KA_LUT_BSEARCH = 2 };
+
+struct KaSolveParams {
+    // problem
+    int T;
+    const int32_t* topic_hash;  // [T]
+    const int64_t* part_off;    // [T+1] or nullptr (dense: P partitions per topic)
+    int P;
+    const int64_t* rep_off;     // [Q+1] or nullptr (dense: RF replicas per row)
+    int RF;
+    const int32_t* cur;         // current replica lists (broker IDs)
+    int desired_rf;
+    int S;                      // row stride of slab / set / out
+    int Pmax;                   // max partitions of any topic (smem sizing)
+    // broker table
+    int N;
+    const uint16_t* blob;       // global: rack16[Npad] | lut16[range_pad] (16B aligned, multiple of 16B)
+    int blob_bytes;             // bytes staged into smem (rack, plus lut when lut_mode == SMEM)
+    int lut_off;                // element offset (uint16) of lut16 inside blob
+    int lut_mode;
+    int min_id;
+    uint32_t range;
+    const uint16_t* glut;       // global lut16 (lut_mode == GLOBAL)
+    const int32_t* broker_id;   // [N] ascending (global)
+    // outputs
+    int32_t* set;               // [Q*S] accepted broker indices, ascending per row, -1 padded
+    uint32_t* meta;             // [Q] len | rotation bits
+    int4* tstatus;              // [T] per-topic error record (written only on error)
+    int* err_topic;             // atomicMin of failing topic index (init = INT_MAX)
+};
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ka_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ka_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ka_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ka_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void ka_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void ka_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ka_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ka_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(ka_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared (non-tensor form). bytes % 16 == 0, both addresses 16B aligned.
+__device__ __forceinline__ void ka_tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ka_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(ka_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ int4 ka_lds_v4_volatile(const int* p) {
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ka_smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void ka_sts_volatile(int* p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ka_smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 ka_ldg_stream_v4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t ka_lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Rotation bits of one topic: (|hash| % k) for k = 2..8 packed above the 4-bit length (KAS:190 applied
+// to the remaining-set sizes of KAS:267). Layout: len[0:4) k2[4] k3[5:7) k4[7:9) k5[9:12) k6[12:15) k7[15:18) k8[18:21)
+__device__ __forceinline__ uint32_t ka_rot_bits(uint32_t habs) {
+    return ((habs % 2u) << 4) | ((habs % 3u) << 5) | ((habs % 4u) << 7) | ((habs % 5u) << 9) | ((habs % 6u) << 12) |
+           ((habs % 7u) << 15) | ((habs % 8u) << 18);
+}
+template <int RS>
+__device__ __forceinline__ int ka_rot_of(uint32_t meta, int k) {
+    // k in [1,RS]; select chain instead of a table so nothing lands in local memory
+    int s = 0;
+    if (k == 2) s = (meta >> 4) & 1u;
+    if (k == 3) s = (meta >> 5) & 3u;
+    if (k == 4) s = (meta >> 7) & 3u;
+    if (RS > 4) {
+        if (k == 5) s = (meta >> 9) & 7u;
+        if (k == 6) s = (meta >> 12) & 7u;
+        if (k == 7) s = (meta >> 15) & 7u;
+        if (k == 8) s = (meta >> 18) & 7u;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel A: sticky fill + orphan spread, one topic per warp, persistent CTAs.
+// ------------------------------------------------------------------------------------------------
+struct KaTab {               // CTA-shared views into the staged broker table
+    const uint16_t* rack;    // [N]
+    const uint16_t* lut;     // [range] (lut_mode == SMEM)
+};
+
+__device__ __forceinline__ uint32_t ka_lookup(int id, const KaTab& tab, const KaSolveParams& p) {
+    if (p.lut_mode == KA_LUT_SMEM) {
+        uint32_t off = (uint32_t)id - (uint32_t)p.min_id;
+        return off < p.range ? (uint32_t)tab.lut[off] : KA_DEAD;
+    } else if (p.lut_mode == KA_LUT_GLOBAL) {
+        uint32_t off = (uint32_t)id - (uint32_t)p.min_id;
+        return off < p.range ? (uint32_t)__ldg(&p.glut[off]) : KA_DEAD;
+    } else {
+        int lo = 0, hi = p.N - 1;
+        while (lo <= hi) {
+            int mid = (lo + hi) >> 1;
+            int v = __ldg(&p.broker_id[mid]);
+            if (v == id) return (uint32_t)mid;
+            if (v < id) lo = mid + 1; else hi = mid - 1;
+        }
+        return KA_DEAD;
+    }
+}
+
+template <typename LoadT>
+__device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, LoadT* load, uint16_t* slab, uint8_t* cnt) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = ka_lanemask_lt();
+    const int S = p.S;
+    const int N = p.N;
+
+    int64_t g0;
+    int P;
+    if (p.part_off) {
+        g0 = p.part_off[t];
+        P = (int)(p.part_off[t + 1] - g0);
+    } else {
+        P = p.P;
+        g0 = (int64_t)t * P;
+    }
+
+    int err = 0, errp = -1, erra = 0, errb = 0;
+
+    // ---- KTA:49-61 replication-factor inference / validation ------------------------------------
+    int rf = p.desired_rf;
+    int maxlen = 0;
+    if (!p.rep_off) {
+        maxlen = P > 0 ? p.RF : 0;
+        if (rf < 0 && P > 0) rf = p.RF;
+    } else {
+        const int64_t* ro = p.rep_off + g0;
+        int first = P > 0 ? (int)(ro[1] - ro[0]) : -1;
+        int mism = 0x7FFFFFFF;
+        for (int pp = lane; pp < P; pp += 32) {
+            int sz = (int)(ro[pp + 1] - ro[pp]);
+            maxlen = max(maxlen, sz);
+            if (sz != first) mism = min(mism, pp);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            maxlen = max(maxlen, __shfl_xor_sync(KA_FULL, maxlen, o));
+            mism = min(mism, __shfl_xor_sync(KA_FULL, mism, o));
+        }
+        if (rf < 0 && P > 0) {
+            rf = first;
+            if (mism != 0x7FFFFFFF) {  // first entry (ascending) whose size differs (KTA:57-60)
+                err = KA_E_RF_MISMATCH;
+                errp = mism;
+                erra = (int)(ro[mism + 1] - ro[mism]);
+            }
+        }
+    }
+    if (!err && !(rf > 0)) err = KA_E_RF_NOT_POSITIVE;          // KTA:65-66
+    if (!err && !(rf <= N)) { err = KA_E_RF_GT_BROKERS; erra = rf; }  // KTA:67-69
+
+    const int32_t h = p.topic_hash[t];
+    const bool hmin = (h == (int32_t)0x80000000);
+    const uint32_t habs = hmin ? 0x80000000u : (uint32_t)(h < 0 ? -h : h);
+
+    if (!err) {
+        // ---- KAS:65-71 capacity: (int)ceil((double)(P*rf) / N) == integer ceil-div for int32 operands
+        const int64_t tot = (int64_t)(int32_t)((uint32_t)P * (uint32_t)rf);
+        const int cap = tot > 0 ? (int)((tot + N - 1) / N) : 0;
+
+        // ---- KAS:73-99 node table: loads start empty -------------------------------------------
+        {
+            uint32_t* lw = reinterpret_cast<uint32_t*>(load);
+            const int words = (N * (int)sizeof(LoadT) + 3) >> 2;
+            for (int i = lane; i < words; i += 32) lw[i] = 0u;
+            uint32_t* cw = reinterpret_cast<uint32_t*>(cnt);
+            for (int i = lane; i < ((P + 3) >> 2); i += 32) cw[i] = 0u;
+        }
+
+        // ---- stage the topic's current assignment as 16-bit broker indices ----------------------
+        if (!p.rep_off) {
+            const int RF = p.RF;
+            const int32_t* src = p.cur + g0 * RF;
+            const int n = P * RF;
+            if (RF == S) {
+                // coalesced, 128-bit vectorised when the slab is 16B aligned
+                const bool al = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n & 3) == 0);
+                if (al) {
+                    const int4* s4 = reinterpret_cast<const int4*>(src);
+                    for (int e = lane; e < (n >> 2); e += 32) {
+                        int4 v = ka_ldg_stream_v4(s4 + e);
+                        uint32_t a = ka_lookup(v.x, tab, p), b = ka_lookup(v.y, tab, p);
+                        uint32_t c = ka_lookup(v.z, tab, p), d = ka_lookup(v.w, tab, p);
+                        uint2 pk = make_uint2(a | (b << 16), c | (d << 16));
+                        *reinterpret_cast<uint2*>(slab + 4 * e) = pk;
+                    }
+                } else {
+                    for (int e = lane; e < n; e += 32) slab[e] = (uint16_t)ka_lookup(__ldg(src + e), tab, p);
+                }
+            } else {
+                for (int e = lane; e < n; e += 32) {
+                    int pp = e / RF, r = e - pp * RF;
+                    slab[pp * S + r] = (uint16_t)ka_lookup(__ldg(src + e), tab, p);
+                }
+                for (int e = lane; e < P * (S - RF); e += 32) {
+                    int pp = e / (S - RF), r = RF + (e - pp * (S - RF));
+                    slab[pp * S + r] = (uint16_t)KA_DEAD;
+                }
+            }
+        } else {
+            const int64_t* ro = p.rep_off + g0;
+            for (int pp = lane; pp < P; pp += 32) {
+                int64_t off = ro[pp];
+                int sz = (int)(ro[pp + 1] - off);
+                for (int r = 0; r < S; ++r)
+                    slab[pp * S + r] = r < sz ? (uint16_t)ka_lookup(__ldg(p.cur + off + r), tab, p) : (uint16_t)KA_DEAD;
+            }
+        }
+        __syncwarp();
+
+        // ---- KAS:101-131 sticky fill: visit order (slot r, partition ascending) ------------------
+        for (int r = 0; r < maxlen; ++r) {
+            for (int c0 = 0; c0 < P; c0 += 32) {
+                const int pp = c0 + lane;
+                const bool valid = pp < P;
+                uint32_t idx = valid ? (uint32_t)slab[pp * S + r] : KA_DEAD;
+                const int k = valid ? (int)cnt[pp] : 0;
+                bool feas = idx != KA_DEAD;
+                if (feas) {
+                    const uint32_t rk = tab.rack[idx];
+                    for (int i = 0; i < k; ++i)  // rack exclusivity (also covers "node already has p")
+                        if (tab.rack[slab[pp * S + i]] == rk) feas = false;
+                }
+                const uint32_t fm = __ballot_sync(KA_FULL, feas);
+                int rank = 0, gsz = 0, l = 0;
+                if (feas) {
+                    // rank among this pass's candidates of the same broker, ascending partition
+                    const uint32_t m = __match_any_sync(fm, idx);
+                    rank = __popc(m & lt);
+                    gsz = __popc(m);
+                    l = (int)load[idx];
+                }
+                __syncwarp();  // every candidate has read the broker's load before anyone updates it
+                if (feas) {
+                    if (l + rank < cap) {
+                        slab[pp * S + k] = (uint16_t)idx;  // in-place compaction: k <= r
+                        cnt[pp] = (uint8_t)(k + 1);
+                    }
+                    if (rank == 0) load[idx] = (LoadT)(l + min(gsz, max(cap - l, 0)));
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- KAS:188-200 rotated processing order ------------------------------------------------
+        uint32_t start = 0;
+        if (!hmin) {
+            start = habs % (uint32_t)N;
+        } else {
+            uint32_t rmd = 0x80000000u % (uint32_t)N;  // Math.abs(MIN_VALUE) % N == -(2^31 % N)
+            if (rmd != 0) { err = KA_E_HASH_INDEX; erra = -(int)rmd; errb = N; }
+        }
+        const int i0 = (int)(((uint32_t)N - start) % (uint32_t)N);  // sorted index at order position 0
+
+        // ---- KAS:133-186 orphans, ascending partition; first-fit from position 0 each time -------
+        int head = 0;  // all order positions < head hold full nodes (loads never decrease)
+        for (int c0 = 0; c0 < P && !err; c0 += 32) {
+            const int pp0 = c0 + lane;
+            const int need = pp0 < P ? rf - (int)cnt[pp0] : 0;
+            uint32_t ob = __ballot_sync(KA_FULL, need > 0);
+            while (ob && !err) {
+                const int src = __ffs(ob) - 1;
+                ob &= ob - 1;
+                const int pp = c0 + src;
+                int rem = __shfl_sync(KA_FULL, need, src);
+                int k = (int)cnt[pp];
+                uint32_t ur[KA_MAX_SLOTS];  // racks already holding this partition (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < KA_MAX_SLOTS; ++i) ur[i] = i < k ? (uint32_t)tab.rack[slab[pp * S + i]] : 0xFFFFFFFFu;
+                bool adv = true;
+                for (int j = head; j < N && rem > 0; j += 32) {
+                    const int pos = j + lane;
+                    int idx = i0 + pos;
+                    if (idx >= N) idx -= N;
+                    bool nonfull = false;
+                    uint32_t rk = 0xFFFFFFFEu;
+                    if (pos < N) {
+                        nonfull = (int)load[idx] < cap;
+                        rk = tab.rack[idx];
+                    }
+                    if (adv) {
+                        const uint32_t nb = __ballot_sync(KA_FULL, nonfull);
+                        if (nb == 0) head = min(j + 32, N);
+                        else { head = j + __ffs(nb) - 1; adv = false; }
+                    }
+                    bool feas = nonfull;
+#pragma unroll
+                    for (int i = 0; i < KA_MAX_SLOTS; ++i) feas = feas && (ur[i] != rk);
+                    uint32_t fb = __ballot_sync(KA_FULL, feas);
+                    while (fb && rem > 0) {
+                        const int f = __ffs(fb) - 1;
+                        const int cidx = __shfl_sync(KA_FULL, idx, f);
+                        const uint32_t crk = __shfl_sync(KA_FULL, rk, f);
+                        if (lane == f) {
+                            load[idx] = (LoadT)((int)load[idx] + 1);
+                            slab[pp * S + k] = (uint16_t)cidx;
+                        }
+#pragma unroll
+                        for (int i = 0; i < KA_MAX_SLOTS; ++i)
+                            if (i == k) ur[i] = crk;
+                        ++k;
+                        --rem;
+                        fb &= ~((2u << f) - 1u);                          // only later positions
+                        fb &= ~__ballot_sync(KA_FULL, rk == crk);        // that rack is now taken
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) cnt[pp] = (uint8_t)k;
+                __syncwarp();
+                if (rem > 0 && !err) { err = KA_E_UNASSIGNABLE; errp = pp; }  // KAS:183-184
+            }
+        }
+
+        // ---- per-partition finalisation: ascending broker order (KAS:205-214) --------------------
+        if (!err) {
+            int firstbad = 0x7FFFFFFF, badk = 0;
+            for (int pp = lane; pp < P; pp += 32) {
+                const int k = (int)cnt[pp];
+                uint16_t* row = slab + pp * S;
+                for (int i = 1; i < k; ++i) {  // insertion sort, k <= 8
+                    uint16_t v = row[i];
+                    int j = i - 1;
+                    while (j >= 0 && row[j] > v) { row[j + 1] = row[j]; --j; }
+                    row[j + 1] = v;
+                }
+                if (hmin && k >= 3 && pp < firstbad) { firstbad = pp; badk = k; }
+            }
+            if (hmin) {  // KAS:267 with Math.abs(MIN_VALUE): first remaining-set size that does not divide 2^31
+                int fb2 = firstbad;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) fb2 = min(fb2, __shfl_xor_sync(KA_FULL, fb2, o));
+                if (fb2 != 0x7FFFFFFF) {
+                    const uint32_t bm = __ballot_sync(KA_FULL, firstbad == fb2);
+                    const int kk = __shfl_sync(KA_FULL, badk, __ffs(bm) - 1);
+                    const int kfail = (kk & (kk - 1)) ? kk : kk - 1;
+                    err = KA_E_HASH_INDEX;
+                    errp = -1;
+                    erra = -(int)(0x80000000u % (uint32_t)kfail);
+                    errb = kfail;
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- emit ------------------------------------------------------------------------------------
+    const uint32_t rot = (err || hmin) ? 0u : ka_rot_bits(habs);
+    int32_t* oset = p.set + g0 * S;
+    if (!err) {
+        for (int e = lane; e < P * S; e += 32) {
+            const int pp = e / S, i = e - pp * S;
+            oset[e] = i < (int)cnt[pp] ? (int32_t)slab[e] : -1;
+        }
+        for (int pp = lane; pp < P; pp += 32) p.meta[g0 + pp] = (uint32_t)cnt[pp] | rot;
+    } else {
+        for (int e = lane; e < P * S; e += 32) oset[e] = -1;
+        for (int pp = lane; pp < P; pp += 32) p.meta[g0 + pp] = 0u;
+        if (lane == 0) {
+            p.tstatus[t] = make_int4(err, errp, erra, errb);
+            atomicMin(p.err_topic, t);
+        }
+    }
+    __syncwarp();
+}
+
+template <typename LoadT>
+__global__ void __launch_bounds__(512) ka_sticky_spread_kernel(const KaSolveParams p, int load_bytes, int slab_bytes, int cnt_bytes) {
+    extern __shared__ __align__(16) unsigned char ka_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ka_smem);
+    unsigned char* blob = ka_smem + 16;
+    unsigned char* warp_base = blob + p.blob_bytes;
+
+    // TMA bulk-stage the broker table (rack indices + id->index LUT) once per CTA.
+    if (threadIdx.x == 0) {
+        ka_mbar_init(bar, 1);
+        ka_fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && p.blob_bytes > 0) {
+        ka_mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
+        ka_tma_bulk_g2s(blob, p.blob, (uint32_t)p.blob_bytes, bar);
+    }
+    if (p.blob_bytes > 0) ka_mbar_wait(bar, 0);
+
+    KaTab tab;
+    tab.rack = reinterpret_cast<const uint16_t*>(blob);
+    tab.lut = reinterpret_cast<const uint16_t*>(blob) + p.lut_off;
+
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int per_warp = load_bytes + slab_bytes + cnt_bytes;
+    unsigned char* mine = warp_base + (size_t)warp * per_warp;
+    LoadT* load = reinterpret_cast<LoadT*>(mine);
+    uint16_t* slab = reinterpret_cast<uint16_t*>(mine + load_bytes);
+    uint8_t* cnt = reinterpret_cast<uint8_t*>(mine + load_bytes + slab_bytes);
+
+    const int total_warps = gridDim.x * nwarp;
+    for (int t = blockIdx.x * nwarp + warp; t < p.T; t += total_warps) ka_solve_topic<LoadT>(p, tab, t, load, slab, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernels T: per-broker occurrence numbering ("tickets") in global partition order.
+//   ticket(q, b) = base(b) + #{ q' < q : b in set(q') },  base(b) = sum of b's counters at entry.
+// Kernel B below may order partition q as soon as, for each of its brokers, the broker's counter row
+// sums to the ticket — i.e. every earlier partition on that broker has committed its increment.
+// Chunks are contiguous ranges of L partitions (L % 32 == 0), one warp per chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ka_ticket_hist_kernel(const int32_t* __restrict__ set, int64_t Q, int S, int N, int64_t L,
+                                                              int num_chunks, int32_t* __restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char ka_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    int* h = reinterpret_cast<int*>(ka_smem) + (size_t)warp * N;
+    for (int c = blockIdx.x * nwarp + warp; c < num_chunks; c += gridDim.x * nwarp) {
+        for (int i = lane; i < N; i += 32) h[i] = 0;
+        __syncwarp();
+        const int64_t e0 = (int64_t)c * L * S;
+        const int64_t e1 = min((int64_t)(c + 1) * L, Q) * S;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int idx = set[e];
+            if (idx >= 0) atomicAdd(&h[idx], 1);
+        }
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) hist[(size_t)c * N + i] = h[i];
+        __syncwarp();
+    }
+}
+
+// Exclusive scan over chunks, per broker, seeded with the broker's current counter-row sum.
+__global__ void ka_ticket_scan_kernel(int32_t* __restrict__ hist, int num_chunks, int N, const int32_t* __restrict__ ctr8, int RS) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    int run = 0;
+    for (int r = 0; r < RS; ++r) run += ctr8[b * KA_MAX_SLOTS + r];
+    for (int c = 0; c < num_chunks; ++c) {
+        const int v = hist[(size_t)c * N + b];
+        hist[(size_t)c * N + b] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(1024) ka_ticket_rank_kernel(const int32_t* __restrict__ set, int64_t Q, int S, int N, int64_t L,
+                                                              int num_chunks, const int32_t* __restrict__ base,
+                                                              int32_t* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char ka_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const uint32_t lt = ka_lanemask_lt();
+    int* issued = reinterpret_cast<int*>(ka_smem) + (size_t)warp * 2 * N;
+    uint32_t* owner = reinterpret_cast<uint32_t*>(issued + N);
+    for (int c = blockIdx.x * nwarp + warp; c < num_chunks; c += gridDim.x * nwarp) {
+        for (int i = lane; i < N; i += 32) { issued[i] = base[(size_t)c * N + i]; owner[i] = 0u; }
+        __syncwarp();
+        const int64_t q0 = (int64_t)c * L, q1 = min((int64_t)(c + 1) * L, Q);
+        for (int64_t qb = q0; qb < q1; qb += 32) {
+            const int64_t q = qb + lane;
+            const bool valid = q < q1;
+            const int32_t* row = set + q * S;
+            int idx[KA_MAX_SLOTS];
+#pragma unroll
+            for (int i = 0; i < KA_MAX_SLOTS; ++i) idx[i] = (valid && i < S) ? row[i] : -1;
+#pragma unroll
+            for (int i = 0; i < KA_MAX_SLOTS; ++i)
+                if (idx[i] >= 0) atomicOr(&owner[idx[i]], 1u << lane);
+            __syncwarp();
+            uint32_t own[KA_MAX_SLOTS];
+#pragma unroll
+            for (int i = 0; i < KA_MAX_SLOTS; ++i) {
+                own[i] = 0u;
+                if (idx[i] >= 0) {
+                    own[i] = owner[idx[i]];
+                    ticket[q * S + i] = issued[idx[i]] + __popc(own[i] & lt);
+                } else if (valid && i < S) {
+                    ticket[q * S + i] = 0;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < KA_MAX_SLOTS; ++i)
+                if (idx[i] >= 0 && (own[i] & lt) == 0u) {  // lowest partition holding this broker in the window
+                    issued[idx[i]] += __popc(own[i]);
+                    owner[idx[i]] = 0u;
+                }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B: leader-preference ordering (KAS:202-239) as an exact dataflow over the counter table.
+// One CTA; counters in shared memory, row-major [N][RS]. Each lane owns one partition of a 32-partition
+// window; a partition commits when all of its brokers' rows have reached its tickets. Windows are taken
+// in global order (warp w: windows w, w+W, ...), so the lowest uncommitted partition is always in flight
+// and always ready: the loop cannot deadlock.
+// ------------------------------------------------------------------------------------------------
+struct KaOrderParams {
+    int64_t Q;
+    int S;
+    int N;
+    const int32_t* set;       // [Q*S]
+    const int32_t* ticket;    // [Q*S]
+    const uint32_t* meta;     // [Q]
+    const int32_t* broker_id; // [N]
+    int32_t* ctr8;            // [N*8] global counters (in/out)
+    int32_t* out;             // [Q*S] broker ids, leader first
+    int32_t* out_len;         // [Q] or nullptr
+    int* err_flag;            // set to KA_E_INTERNAL_SPIN if a window spins beyond the guard
+};
+
+template <int RS>
+__global__ void __launch_bounds__(RS == 4 ? 1024 : 256, 1) ka_leader_order_kernel(const KaOrderParams p) {
+    extern __shared__ __align__(16) unsigned char ka_smem[];
+    int* ctr = reinterpret_cast<int*>(ka_smem);  // [N][RS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int S = p.S;
+
+    for (int i = threadIdx.x; i < p.N * RS; i += blockDim.x) ctr[i] = p.ctr8[(i / RS) * KA_MAX_SLOTS + (i % RS)];
+    __syncthreads();
+
+    const int64_t nwin = (p.Q + 31) >> 5;
+    for (int64_t win = warp; win < nwin; win += nwarp) {
+        const int64_t q = win * 32 + lane;
+        const bool valid = q < p.Q;
+        const uint32_t meta = valid ? p.meta[q] : 0u;
+        const int len = (int)(meta & 15u);
+        int idx[RS], tk[RS];
+#pragma unroll
+        for (int i = 0; i < RS; ++i) {
+            idx[i] = (valid && i < len) ? p.set[q * S + i] : 0;
+            tk[i] = (valid && i < len) ? p.ticket[q * S + i] : 0;
+        }
+        int perm[RS];
+#pragma unroll
+        for (int i = 0; i < RS; ++i) perm[i] = i;
+
+        bool pending = valid && len > 0;
+        uint32_t spins = 0;
+        while (__any_sync(KA_FULL, pending)) {
+            if (pending) {
+                int c[RS][RS];
+                bool ready = true;
+#pragma unroll
+                for (int i = 0; i < RS; ++i) {
+                    if (i < len) {
+                        int sum = 0;
+#pragma unroll
+                        for (int v = 0; v < RS; v += 4) {
+                            int4 rw = ka_lds_v4_volatile(ctr + idx[i] * RS + v);
+                            c[i][v] = rw.x; c[i][v + 1] = rw.y; c[i][v + 2] = rw.z; c[i][v + 3] = rw.w;
+                            sum += rw.x + rw.y + rw.z + rw.w;
+                        }
+                        ready = ready && (sum == tk[i]);
+                    }
+                }
+                if (ready) {
+                    // KAS:226-234: slot r takes, among the remaining brokers (ascending id), the one with the
+                    // least counter[.][r]; ties go to the earliest in the order rotated by |hash| % k (KAS:263-278).
+                    uint32_t remmask = (1u << len) - 1u;
+#pragma unroll
+                    for (int r = 0; r < RS; ++r) {
+                        if (r < len) {
+                            const int k = len - r;
+                            const int s = ka_rot_of<RS>(meta, k);
+                            long long best = 0x7FFFFFFFFFFFFFFFLL;
+                            int bpos = 0;
+#pragma unroll
+                            for (int pos = 0; pos < RS; ++pos) {
+                                if ((remmask >> pos) & 1u) {
+                                    int j = __popc(remmask & ((1u << pos) - 1u)) + s;
+                                    if (j >= k) j -= k;
+                                    const long long key = (long long)c[pos][r] * 8 + j;
+                                    if (key < best) { best = key; bpos = pos; }
+                                }
+                            }
+                            perm[r] = bpos;
+                            remmask &= ~(1u << bpos);
+                        }
+                    }
+                    // KAS:254-261: counter[list[r]][r] += 1 — one store per broker row commits the partition.
+#pragma unroll
+                    for (int r = 0; r < RS; ++r) {
+                        if (r < len) {
+                            int bi = 0, cv = 0;
+#pragma unroll
+                            for (int pos = 0; pos < RS; ++pos)
+                                if (perm[r] == pos) { bi = idx[pos]; cv = c[pos][r]; }
+                            ka_sts_volatile(ctr + bi * RS + r, cv + 1);
+                        }
+                    }
+                    pending = false;
+                }
+            }
+            if (++spins > (1u << 24)) {  // guard: a ticket/set inconsistency must not hang the GPU
+                if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
+                pending = false;
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+                if (r < S) {
+                    int bi = -1;
+#pragma unroll
+                    for (int pos = 0; pos < RS; ++pos)
+                        if (r < len && perm[r] == pos) bi = idx[pos];
+                    p.out[q * S + r] = bi >= 0 ? __ldg(&p.broker_id[bi]) : -1;
+                }
+            }
+            if (p.out_len) p.out_len[q] = len;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.N * RS; i += blockDim.x) p.ctr8[(i / RS) * KA_MAX_SLOTS + (i % RS)] = ctr[i];
+}

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — partition-replica assignments/sec of the B200-native kafka-assigner hot path.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+  torchrun ... bench.py --gpus N ...                       # one rank per GPU, topic-sharded (weak scaling)
+
+A "step" is one pass of the hot path (KafkaTopicAssigner.generateAssignment for every topic of the
+workload, in order, through ONE Context — the loop of KafkaAssignmentGenerator.java:172-184) over one
+batch of synthetic input. `value` times the device-resident solve (inputs already in HBM, outputs left
+in HBM) with CUDA events on the launching stream; `e2e` times the same solve through the host-buffer C-ABI
+call with the H2D and D2H copies inside the timed region. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "partition-replica assignments/sec"
+UNIT = "assignments/s"
+ALGO_BYTES_PER_UNIT = 8  # 4 B current broker read + 4 B new broker written per partition-replica
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons while the timed region runs (NVML; nvidia-smi equivalent)."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def oracle_time(cl, ol, repeats=1):
+    """Seconds for the oracle (single-threaded, like the reference) to solve cluster `cl` `repeats` times."""
+    part_off, part_id, rep_off, cur = cl.ragged()
+    best = []
+    for _ in range(repeats):
+        ctx = ol.OracleContext()
+        t0 = time.perf_counter()
+        ol.run(ctx, cl.topic_names, part_off, part_id, rep_off, cur, cl.broker_id, cl.rack_name, cl.desired_rf, cl.RF)
+        best.append(time.perf_counter() - t0)
+    return best
+
+
+def cpu_sample(cl, ol, budget_s):
+    """Pick a topic prefix of the workload that costs about budget_s of oracle time (pilot on 16 topics)."""
+    n0 = min(cl.T, 16)
+    t = min(oracle_time(cl.subset(0, n0), ol, 2))
+    per_topic = max(t / n0, 1e-7)
+    n = int(max(1, min(cl.T, budget_s / per_topic)))
+    return cl.subset(0, n) if n < cl.T else cl
+
+
+def run_reference(args):
+    """Reference arm: the reference's algorithm (oracle port; no JVM exists in this image) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import kafka_assigner_b200 as kab
+    from oracle import oracle_lib as ol
+    ol.build()
+    cl = kab.synth.make_config(args.workload, args.kind)
+    total = max(1, args.steps + args.warmup)
+    sample = cpu_sample(cl, ol, budget_s=min(20.0, 150.0 / total))
+    for _ in range(args.warmup):
+        oracle_time(sample, ol, 1)
+    ts = []
+    for _ in range(args.steps):
+        ts += oracle_time(sample, ol, 1)
+    sec = float(np.sum(ts))
+    val = sample.replicas * args.steps / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": workload_desc(args.workload, args.kind, cl), "sample": "first %d of %d topics per step" % (sample.T, cl.T)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "first %d of %d topics (%d assignments) per step; single thread like the reference "
+                                   "(KafkaAssignmentGenerator.java:173); host has %d cores" % (sample.T, cl.T, sample.replicas, os.cpu_count())},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "no JVM/javac/jars in this image: the reference Java cannot run; this is oracle/kafka_oracle.cpp, the "
+                "structure-faithful C++ restatement (std::map/std::set for TreeMap/TreeSet)",
+    }
+    print(json.dumps(line))
+
+
+def workload_desc(key, kind, cl):
+    return "%s: %d topics x %d partitions RF=%d, %d brokers / %d racks, %s current assignment (expansion scenario, seed %#x)" % (
+        key, cl.T, cl.P, cl.RF, cl.N, cl.meta.get("R", 0), kind, cl.meta.get("seed", 0))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4shard", "c5"])
+    ap.add_argument("--kind", default="mixed", choices=["mixed", "structured", "random"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import kafka_assigner_b200 as kab
+    from kafka_assigner_b200 import multi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kassign has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- workload: rank r owns topics [r*T, (r+1)*T) of a world*T-topic run (weak scaling) ----------
+    T = kab.synth.CONFIGS[args.workload]["T"]
+    cl = kab.synth.make_config(args.workload, args.kind, t_offset=rank * T)
+    units_rank = cl.replicas
+    units_total = units_rank * world
+    S = cl.RF
+
+    solver = kab.Solver(local)
+    solver.set_brokers(cl.broker_id, cl.rack_index)
+    solver.set_timing(True)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    h_hash = torch.from_numpy(cl.topic_hash).pin_memory()
+    h_cur = torch.from_numpy(cl.cur).pin_memory()
+    h_out = torch.empty((cl.T, cl.P, S), dtype=torch.int32).pin_memory()
+    h_len = torch.empty((cl.T, cl.P), dtype=torch.int32).pin_memory()
+    d_hash = h_hash.cuda()
+    d_cur = h_cur.cuda()
+    d_out = torch.empty((cl.T, cl.P, S), dtype=torch.int32, device="cuda")
+    d_len = torch.empty((cl.T, cl.P), dtype=torch.int32, device="cuda")
+    slots = 8
+    ctr_buf = torch.zeros(cl.N * slots, dtype=torch.int32, device="cuda")
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def stage():
+        solver.stage_dense_device(cl.T, d_hash.data_ptr(), cl.P, cl.RF, d_cur.data_ptr(), -1, S, stream=sptr)
+
+    def order():
+        solver.order_device(d_len.data_ptr(), d_out.data_ptr(), stream=sptr, sync=False)
+
+    def device_step():
+        if world == 1:
+            solver.solve_dense_device(cl.T, d_hash.data_ptr(), cl.P, cl.RF, d_cur.data_ptr(), -1, S, d_len.data_ptr(),
+                                      d_out.data_ptr(), stream=sptr, sync=False)
+        else:
+            multi.ring_solve(rank, world, stage, order, lambda t: solver.export_counters_device(t.data_ptr(), sptr),
+                             lambda t: solver.import_counters_device(t.data_ptr(), sptr), ctr_buf, dist, final_broadcast=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    phase = {"sticky_spread_ms": [], "tickets_ms": [], "leader_order_ms": []}
+
+    def timed_steps(n, record):
+        tot = 0.0
+        for i in range(n):
+            solver.reset()                      # fresh Context per run (untimed)
+            flush.fill_(i & 0xFF)               # evict L2 between iterations (untimed)
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            device_step()
+            e1.record(stream)
+            st = solver.last_status()           # synchronises the stream
+            if st.code != 0:
+                raise SystemExit("solve failed: code %d topic %d" % (st.code, st.topic_index))
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+            if record:
+                tm = solver.last_timing()
+                for k in phase:
+                    phase[k].append(tm[k])
+        return tot
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    timed_steps(args.warmup, False)
+    barrier()
+    launches0 = solver.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = timed_steps(args.steps, True)
+    clocks = sampler.stop()
+    launches = solver.launch_count() - launches0
+    barrier()
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    value = units_total * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end: pinned host buffers -> H2D -> solve -> D2H, every step ---------------------------
+    def e2e_step():
+        if world == 1:
+            out, out_len, st = solver.solve_dense(h_hash.numpy(), h_cur.numpy(), -1, S, out=h_out.numpy(), out_len=h_len.numpy(),
+                                                  check=False)
+            if st.code != 0:
+                raise SystemExit("e2e solve failed: %d" % st.code)
+        else:
+            d_hash.copy_(h_hash, non_blocking=True)
+            d_cur.copy_(h_cur, non_blocking=True)
+            device_step()
+            h_out.copy_(d_out, non_blocking=True)
+            h_len.copy_(d_len, non_blocking=True)
+            st = solver.last_status()
+            if st.code != 0:
+                raise SystemExit("e2e solve failed: %d" % st.code)
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.reset()
+        e2e_step()
+    e2e_s = 0.0
+    for i in range(args.steps):
+        solver.reset()
+        flush.fill_(i & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_s += time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e.item())
+    e2e_val = units_total * args.steps / e2e_s
+    h2d = (h_hash.numel() + h_cur.numel()) * 4
+    d2h = (h_out.numel() + h_len.numel()) * 4
+
+    # ---- roofline of the dominant kernel (CUDA events recorded around each phase by the library) ------
+    peak, peak_src = load_peaks()
+    avg = {k: float(np.mean(v)) for k, v in phase.items()}
+    dom = max(avg, key=avg.get)
+    kname = {"sticky_spread_ms": "ka_sticky_spread_kernel", "tickets_ms": "ka_ticket_* (hist+scan+rank)",
+             "leader_order_ms": "ka_leader_order_kernel"}[dom]
+    algo_bytes = ALGO_BYTES_PER_UNIT * units_rank
+    achieved = algo_bytes / (avg[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(kname)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_ms": avg[dom], "phase_ms": avg,
+                "per_phase_frac": {k: (algo_bytes / (v * 1e-3) / 1e9) / peak for k, v in avg.items() if v > 0},
+                "note": "leader ordering is a serial dependency chain through Context.counter (KAS:202-239); its bound is "
+                        "chain latency, not HBM bandwidth — see DESIGN.md"}
+
+    # ---- verification + CPU baseline (rank 0) ---------------------------------------------------------
+    verified, cpu_baseline = None, None
+    if rank == 0:
+        from oracle import oracle_lib as ol
+        ol.build()
+        if not args.no_verify:
+            sample = cpu_sample(cl, ol, 6.0)
+            part_off, part_id, rep_off, cur = sample.ragged()
+            o_len, _, o_out, _ = ol.run(ol.OracleContext(), sample.topic_names, part_off, part_id, rep_off, cur, sample.broker_id,
+                                        sample.rack_name, -1, S)
+            got = h_out.numpy()[:sample.T].reshape(-1, S)
+            verified = bool(np.array_equal(got, o_out))
+            if not verified:
+                raise SystemExit("bench output differs from the oracle on the first %d topics" % sample.T)
+        if world == 1 and not args.no_cpu_baseline:
+            sample = cpu_sample(cl, ol, 12.0)
+            reps = 3 if sample.T == cl.T else 1
+            ts = oracle_time(sample, ol, reps)
+            cpu_val = sample.replicas / float(np.median(ts))
+            cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": "first %d of %d topics (%d assignments), median of %d run(s), %.2f s each; single thread "
+                                      "like the reference (KafkaAssignmentGenerator.java:173); host has %d cores"
+                                      % (sample.T, cl.T, sample.replicas, reps, float(np.median(ts)), os.cpu_count())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload, args.kind, cl) + ("; x%d topic blocks, one per GPU" % world if world > 1 else ""),
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush); fresh Context per step",
+                       "parallelism": "topic-sharded stage + ring hand-off of Context.counter for the leader-order chain" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host wall clock around the blocking call, max over ranks"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "verified_vs_oracle": verified,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

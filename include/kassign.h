@@ -116,6 +116,18 @@ int32_t ka_solve_dense_device(ka_ctx* ctx, int32_t T, const int32_t* d_topic_has
                               const int32_t* d_cur_broker, int32_t desired_rf, int32_t out_stride,
                               int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st);
 
+/* The same solve split at the only point where topics stop being independent, for topic-sharded
+ * multi-GPU runs:
+ *   ka_stage_dense_device  capacity, sticky fill, orphan spread (KAS:65-200) + per-broker histograms —
+ *                          touches no Context state, so every GPU stages its own topic block concurrently;
+ *   ka_order_device        leader-preference ordering (KAS:202-239) of the staged block against THIS ctx's
+ *                          counters — a serial chain over all topics of the run, so rank g calls it after
+ *                          importing the counters rank g-1 exported (ka_ctx_*_counters_device).
+ * ka_solve_dense_device == stage + order. */
+int32_t ka_stage_dense_device(ka_ctx* ctx, int32_t T, const int32_t* d_topic_hash, int32_t P, int32_t RF,
+                              const int32_t* d_cur_broker, int32_t desired_rf, int32_t out_stride, void* stream);
+int32_t ka_order_device(ka_ctx* ctx, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st);
+
 /* Synchronise the last asynchronous solve and return its status. */
 int32_t ka_last_status(ka_ctx* ctx, ka_status* st);
 

@@ -190,6 +190,25 @@ class Solver:
             return None
         return st
 
+    def stage_dense_device(self, T, d_topic_hash, P, RF, d_cur, desired_rf, out_stride, stream=0):
+        """Context-free stage (KAS:65-200) of a topic block — shards across GPUs."""
+        rc = self._L.ka_stage_dense_device(self._h, int(T), ctypes.c_void_p(d_topic_hash), int(P), int(RF),
+                                           ctypes.c_void_p(d_cur), int(desired_rf), int(out_stride),
+                                           ctypes.c_void_p(stream) if stream else None)
+        if rc:
+            raise KassignError(rc, "ka_stage_dense_device")
+
+    def order_device(self, d_out_len, d_out, stream=0, sync=True):
+        """Leader-order stage (KAS:202-239) of the staged block against this Context's counters."""
+        st = KaStatus()
+        rc = self._L.ka_order_device(self._h, ctypes.c_void_p(d_out_len) if d_out_len else None, ctypes.c_void_p(d_out),
+                                     ctypes.c_void_p(stream) if stream else None, ctypes.byref(st) if sync else None)
+        if not sync:
+            if rc:
+                raise KassignError(rc, "ka_order_device")
+            return None
+        return st
+
     def last_status(self):
         st = KaStatus()
         self._L.ka_last_status(self._h, ctypes.byref(st))

@@ -75,10 +75,17 @@ struct ka_ctx {
     HostPinned* h_pin = nullptr;
     // bookkeeping
     bool timing = false;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};
     float last_ms[8] = {};
     bool ev_valid = false;
     int64_t launches = 0;
+    // staged problem (between the context-free stage and the leader-order stage)
+    bool staged = false;
+    int64_t st_Q = 0;
+    int st_S = 0, st_T = 0;
+    int64_t st_L = 0;
+    int st_chunks = 0, st_RS = 4, st_rank_warps = 1, st_rank_grid = 1;
+    size_t st_rank_smem = 0, st_b_smem = 0;
     // async status
     cudaStream_t last_stream = nullptr;
     bool pending_status = false;
@@ -183,11 +190,13 @@ cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-// Enqueue the whole device pipeline on `s`. All pointers are device pointers.
-int enqueue_pipeline(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const int64_t* d_part_off, int P,
-                     const int64_t* d_rep_off, int RF, const int32_t* d_cur, int desired_rf, int S, int Pmax,
-                     int64_t capmax, int64_t Q, int32_t* d_out, int32_t* d_out_len, ka_status* st) {
+// Stage 1 (context-free, shards across GPUs): kernel A + per-chunk broker histograms. All pointers are
+// device pointers. Leaves the sorted replica sets in ctx scratch for enqueue_order().
+int enqueue_stage(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const int64_t* d_part_off, int P,
+                  const int64_t* d_rep_off, int RF, const int32_t* d_cur, int desired_rf, int S, int Pmax,
+                  int64_t capmax, int64_t Q, ka_status* st) {
     Plan pl;
+    c->staged = false;
     int rc = make_plan(c, Q, S, Pmax, capmax, pl, st);
     if (rc != KA_OK) return rc;
     const int N = c->N;
@@ -261,16 +270,40 @@ int enqueue_pipeline(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, co
 
     if (Q > 0 && N > 0) {
         KA_CUDA(allow_smem(ka_ticket_hist_kernel, pl.t_smem_hist));
-        KA_CUDA(allow_smem(ka_ticket_rank_kernel, pl.t_smem_rank));
         ka_ticket_hist_kernel<<<pl.t_grid_hist, pl.t_warps_hist * 32, pl.t_smem_hist, s>>>(c->d_set.as<int32_t>(), Q, S, N, pl.L, pl.num_chunks,
                                                                                             c->d_hist.as<int32_t>());
         KA_CUDA(cudaGetLastError());
-        ka_ticket_scan_kernel<<<(N + 255) / 256, 256, 0, s>>>(c->d_hist.as<int32_t>(), pl.num_chunks, N, c->d_ctr8.as<int32_t>(), pl.RS);
+        c->launches++;
+    }
+    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[6], s));
+    c->staged = true;
+    c->st_Q = Q;
+    c->st_S = S;
+    c->st_T = T;
+    c->st_L = pl.L;
+    c->st_chunks = pl.num_chunks;
+    c->st_RS = pl.RS;
+    c->st_rank_warps = pl.t_warps_rank;
+    c->st_rank_grid = pl.t_grid_rank;
+    c->st_rank_smem = pl.t_smem_rank;
+    c->st_b_smem = pl.b_smem;
+    return KA_OK;
+}
+
+// Stage 2 (the serial chain through Context.counter, KAS:202-239): ticket scan + rank, then kernel B.
+int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len, ka_status* st) {
+    if (!c->staged) return set_status(st, KA_ERR_BAD_ARG);
+    const int N = c->N, S = c->st_S;
+    const int64_t Q = c->st_Q;
+    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[7], s));
+    if (Q > 0 && N > 0) {
+        KA_CUDA(allow_smem(ka_ticket_rank_kernel, c->st_rank_smem));
+        ka_ticket_scan_kernel<<<(N + 255) / 256, 256, 0, s>>>(c->d_hist.as<int32_t>(), c->st_chunks, N, c->d_ctr8.as<int32_t>(), c->st_RS);
         KA_CUDA(cudaGetLastError());
-        ka_ticket_rank_kernel<<<pl.t_grid_rank, pl.t_warps_rank * 32, pl.t_smem_rank, s>>>(c->d_set.as<int32_t>(), Q, S, N, pl.L, pl.num_chunks,
-                                                                                            c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>());
+        ka_ticket_rank_kernel<<<c->st_rank_grid, c->st_rank_warps * 32, c->st_rank_smem, s>>>(
+            c->d_set.as<int32_t>(), Q, S, N, c->st_L, c->st_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>());
         KA_CUDA(cudaGetLastError());
-        c->launches += 3;
+        c->launches += 2;
     }
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
 
@@ -287,21 +320,30 @@ int enqueue_pipeline(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, co
         o.out = d_out;
         o.out_len = d_out_len;
         o.err_flag = c->d_flags.as<int>() + 1;
-        if (pl.RS == 4) {
-            KA_CUDA(allow_smem(ka_leader_order_kernel<4>, pl.b_smem));
-            ka_leader_order_kernel<4><<<1, 1024, pl.b_smem, s>>>(o);
+        if (c->st_RS == 4) {
+            KA_CUDA(allow_smem(ka_leader_order_kernel<4>, c->st_b_smem));
+            ka_leader_order_kernel<4><<<1, 1024, c->st_b_smem, s>>>(o);
         } else {
-            KA_CUDA(allow_smem(ka_leader_order_kernel<8>, pl.b_smem));
-            ka_leader_order_kernel<8><<<1, 256, pl.b_smem, s>>>(o);
+            KA_CUDA(allow_smem(ka_leader_order_kernel<8>, c->st_b_smem));
+            ka_leader_order_kernel<8><<<1, 256, c->st_b_smem, s>>>(o);
         }
         KA_CUDA(cudaGetLastError());
         c->launches++;
     }
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
+    c->staged = false;
 
     // status words back to pinned host memory (async)
     KA_CUDA(cudaMemcpyAsync(&c->h_pin->err_topic, c->d_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     return KA_OK;
+}
+
+int enqueue_pipeline(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const int64_t* d_part_off, int P,
+                     const int64_t* d_rep_off, int RF, const int32_t* d_cur, int desired_rf, int S, int Pmax,
+                     int64_t capmax, int64_t Q, int32_t* d_out, int32_t* d_out_len, ka_status* st) {
+    int rc = enqueue_stage(c, s, T, d_hash, d_part_off, P, d_rep_off, RF, d_cur, desired_rf, S, Pmax, capmax, Q, st);
+    if (rc != KA_OK) return rc;
+    return enqueue_order(c, s, d_out, d_out_len, st);
 }
 
 // Wait for the stream, translate device flags into a ka_status.
@@ -330,7 +372,10 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
         for (int i = 0; i < 8; ++i) c->last_ms[i] = 0.f;
         cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]);  // H2D
         cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]);  // kernel A
-        cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);  // tickets
+        float t1 = 0.f, t2 = 0.f;
+        cudaEventElapsedTime(&t1, c->ev[2], c->ev[6]);             // ticket histogram (stage 1)
+        cudaEventElapsedTime(&t2, c->ev[7], c->ev[3]);             // ticket scan + rank (stage 2)
+        c->last_ms[1] = t1 + t2;
         cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);  // kernel B
         cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);  // D2H
         cudaEventElapsedTime(&c->last_ms[5], c->ev[0], c->ev[5]);  // total
@@ -574,6 +619,36 @@ int32_t ka_solve_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     if (c->timing) { cudaEventRecord(c->ev[0], s); }
     rc = enqueue_pipeline(c, s, T, d_topic_hash, nullptr, P, nullptr, RF, d_cur_broker, desired_rf, out_stride, P, capmax, Q,
                           d_out_broker, d_out_len, st);
+    if (rc != KA_OK) return rc;
+    if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
+    c->last_stream = s;
+    c->pending_status = true;
+    if (st) return finish_status(c, s, st);
+    return KA_OK;
+}
+
+int32_t ka_stage_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash, int32_t P, int32_t RF,
+                              const int32_t* d_cur_broker, int32_t desired_rf, int32_t out_stride, void* stream) {
+    ka_status lst;
+    int rc = validate_dense(c, T, P, RF, desired_rf, out_stride, &lst);
+    if (rc != KA_OK) return rc;
+    if (cudaSetDevice(c->device) != cudaSuccess) return KA_ERR_CUDA;
+    if (c->pending_status) finish_status(c, c->last_stream, nullptr);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t Q = (int64_t)T * P;
+    const int rf_t = desired_rf >= 0 ? desired_rf : RF;
+    const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
+    c->last_part_id = nullptr;
+    c->last_part_off = nullptr;
+    if (c->timing) { cudaEventRecord(c->ev[0], s); }
+    return enqueue_stage(c, s, T, d_topic_hash, nullptr, P, nullptr, RF, d_cur_broker, desired_rf, out_stride, P, capmax, Q, &lst);
+}
+
+int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st) {
+    if (!c) return set_status(st, KA_ERR_NO_DEVICE);
+    if (cudaSetDevice(c->device) != cudaSuccess) return set_status(st, KA_ERR_CUDA);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = enqueue_order(c, s, d_out_broker, d_out_len, st);
     if (rc != KA_OK) return rc;
     if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
     c->last_stream = s;

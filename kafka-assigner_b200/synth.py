@@ -93,7 +93,7 @@ def rack_indices(broker_id, rack_name):
 
 
 def make_cluster(T, P, RF, N, R, seed, kind="mixed", n_old=None, remove_frac=0.0, name=None,
-                 rack_aware=True, topic_prefix="topic-"):
+                 rack_aware=True, topic_prefix="topic-", t_offset=0):
     """Expansion / decommission scenario of SURVEY §8d.
 
     brokers: ids 1000+i, rack of broker i = i % R ("r%02d"); the CURRENT assignment lives on the first
@@ -101,6 +101,8 @@ def make_cluster(T, P, RF, N, R, seed, kind="mixed", n_old=None, remove_frac=0.0
     minus, per rack, the round(remove_frac*N/R) highest-ordinal brokers.
     kind: "structured" cur[t,p,r] = old[(s_t + RF*p + r) % n_old]; "random" = RF distinct racks, uniform
     broker inside each, random order; "mixed" = even topics structured, odd topics random.
+    t_offset: generate topics [t_offset, t_offset+T) of a longer run (names, hashes and random streams are
+    indexed by the GLOBAL topic number, so shards of one job can be generated independently per rank).
     """
     assert R >= RF and N >= R
     if n_old is None:
@@ -119,11 +121,11 @@ def make_cluster(T, P, RF, N, R, seed, kind="mixed", n_old=None, remove_frac=0.0
     live_ids = all_ids[live_mask]
     rack_names = ["r%02d" % (i % R) if rack_aware else None for i in ordinal[live_mask]]
 
-    names = ["%s%06d" % (topic_prefix, t) for t in range(T)]
+    names = ["%s%06d" % (topic_prefix, t) for t in range(t_offset, t_offset + T)]
     th = java_string_hash_ascii(names)
     assert not np.any(th == np.int32(-2**31)), "synthetic topic name hashes to Integer.MIN_VALUE"
 
-    t_idx = np.arange(T, dtype=np.uint64)
+    t_idx = np.arange(t_offset, t_offset + T, dtype=np.uint64)
     s_t = (splitmix64(seed, t_idx) % np.uint64(n_old)).astype(np.int64)  # per-topic offset
     cur = np.empty((T, P, RF), dtype=np.int32)
     p_idx = np.arange(P, dtype=np.int64)
@@ -136,7 +138,7 @@ def make_cluster(T, P, RF, N, R, seed, kind="mixed", n_old=None, remove_frac=0.0
         per_rack_old = n_old // R
         for t0 in range(0, T, chunk):
             t1 = min(T, t0 + chunk)
-            tt = np.arange(t0, t1, dtype=np.uint64)
+            tt = np.arange(t_offset + t0, t_offset + t1, dtype=np.uint64)
             base = ((tt[:, None] * np.uint64(P) + np.arange(P, dtype=np.uint64)[None, :]) * np.uint64(16)) + np.uint64(1 << 40)
             racks = np.empty((t1 - t0, P, RF), dtype=np.int64)
             for r in range(RF):
@@ -153,7 +155,7 @@ def make_cluster(T, P, RF, N, R, seed, kind="mixed", n_old=None, remove_frac=0.0
                 cur[t0:t1] = rnd
             else:  # mixed
                 cur[t0:t1] = all_ids[structured[t0:t1]]
-                odd = (np.arange(t0, t1) % 2) == 1
+                odd = (np.arange(t_offset + t0, t_offset + t1) % 2) == 1
                 cur[t0:t1][odd] = rnd[odd]
     ri = rack_indices(live_ids, rack_names)
     return Cluster(name or "T%d_P%d_RF%d_N%d_R%d_%s" % (T, P, RF, N, R, kind), names, th, P, RF, cur, live_ids,

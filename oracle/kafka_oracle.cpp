@@ -378,6 +378,11 @@ int32_t oracle_ctx_get_counter(void* c, int32_t broker_id, int32_t slot) {
     return jt == it->second.end() ? 0 : jt->second;
 }
 
+// Seed Context.counter[brokerId][slot] — lets a test hand a Context from one process to another.
+void oracle_ctx_set_counter(void* c, int32_t broker_id, int32_t slot, int32_t value) {
+    ((Context*)c)->counter[broker_id][slot] = value;
+}
+
 // The KAG:172-184 loop: topics in order through ONE assigner/Context; stops at the first exception.
 //   topic_names: T NUL-terminated UTF-8 strings, concatenated; name_off[T+1] byte offsets (incl. NULs)
 //   part_off[T+1]: partition ranges; part_id[ΣP]: partition ids in the ENTRY ORDER of the input map

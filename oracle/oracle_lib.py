@@ -41,6 +41,8 @@ def lib():
         L.oracle_java_string_hash.restype = ctypes.c_int32
         L.oracle_ctx_get_counter.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
         L.oracle_ctx_get_counter.restype = ctypes.c_int32
+        L.oracle_ctx_set_counter.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.oracle_ctx_set_counter.restype = None
         L.oracle_run.restype = ctypes.c_int
         _lib = L
     return _lib

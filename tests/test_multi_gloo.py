@@ -1,0 +1,113 @@
+"""CPU tests of the N>1 host logic: topic sharding + the ring hand-off of Context.counter, run as a real
+world_size-2 torch.distributed job on the gloo backend. The compute backend is injected into
+multi.ring_solve; here it is the oracle (tests may use it), so the test checks the PROTOCOL: blocks staged
+independently, leader ordering chained rank 0 -> rank 1 through the counter tensor, final broadcast — and
+that the concatenated result equals one single-process run over all topics."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+import kafka_assigner_b200 as kab
+from kafka_assigner_b200 import multi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import kafka_assigner_b200 as kab
+from kafka_assigner_b200 import multi
+from oracle import oracle_lib as ol
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+T_total = 13
+full = kab.synth.make_cluster(T=T_total, P=12, RF=3, N=20, R=5, seed=77, kind="mixed")
+t0, t1 = multi.shard_range(T_total, world, rank)
+mine = kab.synth.make_cluster(T=t1 - t0, P=12, RF=3, N=20, R=5, seed=77, kind="mixed", t_offset=t0)
+assert np.array_equal(mine.cur, full.cur[t0:t1])
+slots = 8
+ctx = ol.OracleContext()
+state = {}
+
+def stage():            # context-free stage: nothing to precompute for the oracle stand-in
+    state["staged"] = True
+
+def order():
+    po, pid, ro, cur = mine.ragged()
+    ln, _, out, st = ol.run(ctx, mine.topic_names, po, pid, ro, cur, mine.broker_id, mine.rack_name, -1, 3)
+    state["out"] = out
+
+def export_counters(t):
+    for i, b in enumerate(mine.broker_id):
+        for s in range(3):
+            t[i * slots + s] = ctx.counter(int(b), s)
+
+def import_counters(t):
+    # rebuild the oracle Context from the tensor by replaying increments is impossible; instead seed a
+    # fresh context through the library's own setter
+    import ctypes
+    ctx.reset()
+    state["seed"] = t.clone()
+    L = ol.lib()
+    for i, b in enumerate(mine.broker_id):
+        for s in range(3):
+            v = int(t[i * slots + s])
+            if v:
+                L.oracle_ctx_set_counter(ctx._h, int(b), s, v)
+
+buf = torch.zeros(20 * slots, dtype=torch.int32)
+multi.ring_solve(rank, world, stage, order, export_counters, import_counters, buf, dist)
+np.save(os.path.join(%(out)r, "out_%%d.npy" %% rank), state["out"])
+np.save(os.path.join(%(out)r, "ctr_%%d.npy" %% rank), buf.numpy())
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_range_covers_everything():
+    for total in (0, 1, 7, 13, 1000):
+        for world in (1, 2, 3, 8):
+            blocks = [multi.shard_range(total, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            for a, b in zip(blocks, blocks[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_ring_handoff_world2_gloo(tmp_path, oracle):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "out": str(tmp_path)})
+    port = _free_port()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    full = kab.synth.make_cluster(T=13, P=12, RF=3, N=20, R=5, seed=77, kind="mixed")
+    po, pid, ro, cur = full.ragged()
+    octx = oracle.OracleContext()
+    ln, _, exp, st = oracle.run(octx, full.topic_names, po, pid, ro, cur, full.broker_id, full.rack_name, -1, 3)
+    got = np.concatenate([np.load(tmp_path / "out_0.npy"), np.load(tmp_path / "out_1.npy")])
+    assert np.array_equal(got, exp)
+    # after the final broadcast both ranks hold the Context of the whole run
+    c0, c1 = np.load(tmp_path / "ctr_0.npy"), np.load(tmp_path / "ctr_1.npy")
+    assert np.array_equal(c0, c1)
+    for i, b in enumerate(full.broker_id):
+        for s in range(3):
+            assert c0[i * 8 + s] == octx.counter(int(b), s)

@@ -47,7 +47,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake": 0x80, "sync_boost": 0x10}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}

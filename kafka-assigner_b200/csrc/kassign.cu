@@ -79,6 +79,7 @@ struct ka_ctx {
     float last_ms[8] = {};
     bool ev_valid = false;
     int64_t launches = 0;
+    int order_threads = 1024;  // leader-order CTA size (KA_ORDER_THREADS overrides; tuning knob)
     // staged problem (between the context-free stage and the leader-order stage)
     bool staged = false;
     int64_t st_Q = 0;
@@ -320,12 +321,26 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         o.out = d_out;
         o.out_len = d_out_len;
         o.err_flag = c->d_flags.as<int>() + 1;
+        int nt = c->order_threads;
+        if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
+        o.sleep_ns = 48;
+        o.near_dist = 1;
+        if (const char* e = std::getenv("KA_ORDER_SLEEP_NS")) o.sleep_ns = (unsigned)std::atoi(e);
+        if (const char* e = std::getenv("KA_ORDER_NEAR")) o.near_dist = std::atoi(e);
         if (c->st_RS == 4) {
-            KA_CUDA(allow_smem(ka_leader_order_kernel<4>, c->st_b_smem));
-            ka_leader_order_kernel<4><<<1, 1024, c->st_b_smem, s>>>(o);
+#define KA_LAUNCH_ORDER4(NT)                                                        \
+    do {                                                                            \
+        KA_CUDA(allow_smem(ka_leader_order4_kernel<NT>, c->st_b_smem));             \
+        ka_leader_order4_kernel<NT><<<1, NT, c->st_b_smem, s>>>(o);                 \
+    } while (0)
+            if (nt >= 1024) KA_LAUNCH_ORDER4(1024);
+            else if (nt >= 512) KA_LAUNCH_ORDER4(512);
+            else if (nt >= 256) KA_LAUNCH_ORDER4(256);
+            else KA_LAUNCH_ORDER4(128);
+#undef KA_LAUNCH_ORDER4
         } else {
-            KA_CUDA(allow_smem(ka_leader_order_kernel<8>, c->st_b_smem));
-            ka_leader_order_kernel<8><<<1, 256, c->st_b_smem, s>>>(o);
+            KA_CUDA(allow_smem(ka_leader_order_kernel<8, 256>, c->st_b_smem));
+            ka_leader_order_kernel<8, 256><<<1, 256, c->st_b_smem, s>>>(o);
         }
         KA_CUDA(cudaGetLastError());
         c->launches++;

@@ -569,10 +569,235 @@ struct KaOrderParams {
     int32_t* out;             // [Q*S] broker ids, leader first
     int32_t* out_len;         // [Q] or nullptr
     int* err_flag;            // set to KA_E_INTERNAL_SPIN if a window spins beyond the guard
+    unsigned sleep_ns;        // back-off of warps with no partition near its turn (0 = spin)
+    int near_dist;            // "near" = at most this many commits away on the slowest broker
 };
 
+// ------------------------------------------------------------------------------------------------
+// Kernel B, specialised for rows of 4 slots (every partition list <= 4 replicas: all BASELINE configs).
+// Written with explicit scalars — no arrays — so that every selection compiles to SEL/predication and
+// nothing is spilled to (or dynamically indexed in) local memory.
+// ------------------------------------------------------------------------------------------------
+#define KA_BIG 0x7FFFFFFF
+
+__device__ __forceinline__ int ka_sel4(int k, int a0, int a1, int a2, int a3) {
+    return k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+}
+
+// One selection round of KAS:263-278 over the remaining positions `rem` (bitmask over the ascending
+// broker list), counters cv0..cv3 = counter[broker at pos][slot of this round], rotation s, k = popc(rem).
+__device__ __forceinline__ int ka_pick4(uint32_t rem, int k, int s, int cv0, int cv1, int cv2, int cv3) {
+    long long best = 0x7FFFFFFFFFFFFFFFLL;
+    int bpos = 0;
+    {
+        int j = s; if (j >= k) j -= k;
+        const long long key = (long long)cv0 * 8 + j;
+        if ((rem & 1u) && key < best) { best = key; bpos = 0; }
+    }
+    {
+        int j = __popc(rem & 1u) + s; if (j >= k) j -= k;
+        const long long key = (long long)cv1 * 8 + j;
+        if ((rem & 2u) && key < best) { best = key; bpos = 1; }
+    }
+    {
+        int j = __popc(rem & 3u) + s; if (j >= k) j -= k;
+        const long long key = (long long)cv2 * 8 + j;
+        if ((rem & 4u) && key < best) { best = key; bpos = 2; }
+    }
+    {
+        int j = __popc(rem & 7u) + s; if (j >= k) j -= k;
+        const long long key = (long long)cv3 * 8 + j;
+        if ((rem & 8u) && key < best) { best = key; bpos = 3; }
+    }
+    return bpos;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) ka_leader_order4_kernel(const KaOrderParams p) {
+    extern __shared__ __align__(16) unsigned char ka_smem[];
+    int* ctr = reinterpret_cast<int*>(ka_smem);  // [N][4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int S = p.S;
+
+    for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) ctr[i] = p.ctr8[(i >> 2) * KA_MAX_SLOTS + (i & 3)];
+    __syncthreads();
+
+    const int64_t nwin = (p.Q + 31) >> 5;
+    // software prefetch of the next window's inputs: global latency stays off the dependency chain
+    uint32_t n_meta = 0u;
+    int n_i0 = 0, n_i1 = 0, n_i2 = 0, n_i3 = 0, n_t0 = 0, n_t1 = 0, n_t2 = 0, n_t3 = 0;
+    auto fetch = [&](int64_t win) {
+        const int64_t q = win * 32 + lane;
+        n_meta = 0u;
+        if (win < nwin && q < p.Q) {
+            n_meta = __ldg(p.meta + q);
+            const int32_t* sp = p.set + q * S;
+            const int32_t* tp = p.ticket + q * S;
+            n_i0 = __ldg(sp); n_t0 = __ldg(tp);
+            if (S > 1) { n_i1 = __ldg(sp + 1); n_t1 = __ldg(tp + 1); }
+            if (S > 2) { n_i2 = __ldg(sp + 2); n_t2 = __ldg(tp + 2); }
+            if (S > 3) { n_i3 = __ldg(sp + 3); n_t3 = __ldg(tp + 3); }
+        }
+    };
+    fetch(warp);
+
+    for (int64_t win = warp; win < nwin; win += nwarp) {
+        const int64_t q = win * 32 + lane;
+        const bool valid = q < p.Q;
+        const uint32_t meta = n_meta;
+        const int len = (int)(meta & 15u);
+        // shared-memory byte offsets of this partition's broker rows (clamped for unused slots)
+        const int a0 = (len > 0 ? max(n_i0, 0) : 0) * 16, a1 = (len > 1 ? max(n_i1, 0) : 0) * 16;
+        const int a2 = (len > 2 ? max(n_i2, 0) : 0) * 16, a3 = (len > 3 ? max(n_i3, 0) : 0) * 16;
+        const int t0 = n_t0, t1 = n_t1, t2 = n_t2, t3 = n_t3;
+        fetch(win + nwarp);
+
+        const int s2 = (int)((meta >> 4) & 1u), s3 = (int)((meta >> 5) & 3u), s4 = (int)((meta >> 7) & 3u);
+        // RF=3 tie-breaks, independent of the counters (computed while waiting): rotated scan position of list
+        // position i is j_i = (i + s3) % 3; t_xy = [j_x < j_y].
+        const int j0 = s3, j1 = (s3 + 1 >= 3) ? s3 - 2 : s3 + 1, j2 = (s3 + 2 >= 3) ? s3 - 1 : s3 + 2;
+        const int t10 = j1 < j0 ? 1 : 0, t20 = j2 < j0 ? 1 : 0, t21 = j2 < j1 ? 1 : 0;
+        int b0 = 0, b1 = 1, b2 = 2, b3 = 3;  // chosen list position per slot
+        bool pending = valid && len > 0;
+        uint32_t spins = 0;
+        const char* cb = reinterpret_cast<const char*>(ctr);
+        for (;;) {
+            int d = KA_BIG;
+            if (pending) {
+                // Read every broker row of the partition back-to-back (rows that already reached the ticket
+                // are stable until this partition commits, so re-reading them is harmless) ...
+                const int4 r0 = ka_lds_v4_volatile(reinterpret_cast<const int*>(cb + a0));
+                const int4 r1 = ka_lds_v4_volatile(reinterpret_cast<const int*>(cb + a1));
+                const int4 r2 = ka_lds_v4_volatile(reinterpret_cast<const int*>(cb + a2));
+                int4 r3 = make_int4(0, 0, 0, 0);
+                if (S > 3) r3 = ka_lds_v4_volatile(reinterpret_cast<const int*>(cb + a3));
+                // ... distance = commits still to land on the slowest broker before it is this partition's turn
+                d = t0 - (r0.x + r0.y + r0.z + r0.w);
+                if (len > 1) d = max(d, t1 - (r1.x + r1.y + r1.z + r1.w));
+                if (len > 2) d = max(d, t2 - (r2.x + r2.y + r2.z + r2.w));
+                if (len > 3) d = max(d, t3 - (r3.x + r3.y + r3.z + r3.w));
+                if (d == 0) {
+                    // every broker of this partition has reached its ticket: order it (KAS:226-234) and commit
+                    // counter[list[r]][r] += 1 (KAS:254-261) — one store per broker row.
+                    if (len == 3) {
+                        // RF = 3, branch-free. (c, j) lexicographic compare == c_x < c_y + [j_x < j_y].
+                        const bool lt10 = r1.x < r0.x + t10;
+                        const int m = lt10 ? 1 : 0;
+                        const int cm = lt10 ? r1.x : r0.x;
+                        const bool lt2m = r2.x < cm + (lt10 ? t21 : t20);
+                        b0 = lt2m ? 2 : m;
+                        const int v0 = lt2m ? r2.x : cm;
+                        // slot 1: remaining positions pa < pb; rotation s2 decides who is scanned first (wins ties)
+                        const int pa = (b0 == 0) ? 1 : 0, pb = (b0 == 2) ? 1 : 2;
+                        const int ca = (b0 == 0) ? r1.y : r0.y;
+                        const int cbv = (b0 == 2) ? r1.y : r2.y;
+                        const bool pickb = s2 ? !(ca < cbv) : (cbv < ca);
+                        b1 = pickb ? pb : pa;
+                        const int v1 = pickb ? cbv : ca;
+                        b2 = 3 - b0 - b1;
+                        const int ad0 = (b0 == 0) ? a0 : ((b0 == 1) ? a1 : a2);
+                        const int ad1 = (b1 == 0) ? a0 : ((b1 == 1) ? a1 : a2);
+                        const int ad2 = (b2 == 0) ? a0 : ((b2 == 1) ? a1 : a2);
+                        const int v2 = (b2 == 0) ? r0.z : ((b2 == 1) ? r1.z : r2.z);
+                        ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad0), v0 + 1);
+                        ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad1 + 4), v1 + 1);
+                        ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad2 + 8), v2 + 1);
+                    } else {
+                        uint32_t rem = (1u << len) - 1u;
+                        int k = len;
+                        b0 = ka_pick4(rem, k, k == 4 ? s4 : (k == 3 ? s3 : (k == 2 ? s2 : 0)), r0.x, r1.x, r2.x, r3.x);
+                        rem &= ~(1u << b0); --k;
+                        if (k > 0) {
+                            b1 = ka_pick4(rem, k, k == 3 ? s3 : (k == 2 ? s2 : 0), r0.y, r1.y, r2.y, r3.y);
+                            rem &= ~(1u << b1); --k;
+                        }
+                        if (k > 0) {
+                            b2 = ka_pick4(rem, k, k == 2 ? s2 : 0, r0.z, r1.z, r2.z, r3.z);
+                            rem &= ~(1u << b2); --k;
+                        }
+                        if (k > 0) b3 = __ffs(rem) - 1;
+                        {
+                            const int ad = ka_sel4(b0, a0, a1, a2, a3);
+                            const int cv = ka_sel4(b0, r0.x, r1.x, r2.x, r3.x);
+                            ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad), cv + 1);
+                        }
+                        if (len > 1) {
+                            const int ad = ka_sel4(b1, a0, a1, a2, a3);
+                            const int cv = ka_sel4(b1, r0.y, r1.y, r2.y, r3.y);
+                            ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad + 4), cv + 1);
+                        }
+                        if (len > 2) {
+                            const int ad = ka_sel4(b2, a0, a1, a2, a3);
+                            const int cv = ka_sel4(b2, r0.z, r1.z, r2.z, r3.z);
+                            ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad + 8), cv + 1);
+                        }
+                        if (len > 3) {
+                            const int ad = ka_sel4(b3, a0, a1, a2, a3);
+                            const int cv = ka_sel4(b3, r0.w, r1.w, r2.w, r3.w);
+                            ka_sts_volatile(reinterpret_cast<int*>(const_cast<char*>(cb) + ad + 12), cv + 1);
+                        }
+                    }
+                    pending = false;
+                }
+            }
+            const uint32_t pend = __ballot_sync(KA_FULL, pending);
+            if (pend == 0u) break;  // every lane of the window has committed
+            const uint32_t near = __ballot_sync(KA_FULL, pending && d <= p.near_dist);
+            if (near == 0u && p.sleep_ns > 0) {
+                // nobody in this warp can commit before more commits land on its brokers: yield the issue slots
+                // and the shared-memory port to the warps at the frontier.
+                __nanosleep(p.sleep_ns);
+            }
+            if (++spins > (1u << 22)) {  // guard: a ticket/set inconsistency must not hang the GPU
+                if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
+                break;
+            }
+        }
+        if (valid) {
+            const int i0 = ka_sel4(b0, a0, a1, a2, a3) >> 4, i1 = ka_sel4(b1, a0, a1, a2, a3) >> 4;
+            const int i2 = ka_sel4(b2, a0, a1, a2, a3) >> 4, i3 = ka_sel4(b3, a0, a1, a2, a3) >> 4;
+            int32_t* o = p.out + q * S;
+            o[0] = len > 0 ? __ldg(&p.broker_id[i0]) : -1;
+            if (S > 1) o[1] = len > 1 ? __ldg(&p.broker_id[i1]) : -1;
+            if (S > 2) o[2] = len > 2 ? __ldg(&p.broker_id[i2]) : -1;
+            if (S > 3) o[3] = len > 3 ? __ldg(&p.broker_id[i3]) : -1;
+            if (p.out_len) p.out_len[q] = len;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) p.ctr8[(i >> 2) * KA_MAX_SLOTS + (i & 3)] = ctr[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B, generic row width (lists of 5..8 replicas — rare): array-based, correctness first.
+// ------------------------------------------------------------------------------------------------
 template <int RS>
-__global__ void __launch_bounds__(RS == 4 ? 1024 : 256, 1) ka_leader_order_kernel(const KaOrderParams p) {
+__device__ __forceinline__ void ka_order_generic(const int (&c)[RS][RS], int len, uint32_t meta, int (&perm)[RS]) {
+    uint32_t remmask = (1u << len) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+        if (r < len) {
+            const int k = len - r;
+            const int s = ka_rot_of<RS>(meta, k);
+            long long best = 0x7FFFFFFFFFFFFFFFLL;
+            int bpos = 0;
+#pragma unroll
+            for (int pos = 0; pos < RS; ++pos) {
+                if ((remmask >> pos) & 1u) {
+                    int j = __popc(remmask & ((1u << pos) - 1u)) + s;
+                    if (j >= k) j -= k;
+                    const long long key = (long long)c[pos][r] * 8 + j;
+                    if (key < best) { best = key; bpos = pos; }
+                }
+            }
+            perm[r] = bpos;
+            remmask &= ~(1u << bpos);
+        }
+    }
+}
+
+template <int RS, int NT>
+__global__ void __launch_bounds__(NT, 1) ka_leader_order_kernel(const KaOrderParams p) {
     extern __shared__ __align__(16) unsigned char ka_smem[];
     int* ctr = reinterpret_cast<int*>(ka_smem);  // [N][RS]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -590,13 +815,12 @@ __global__ void __launch_bounds__(RS == 4 ? 1024 : 256, 1) ka_leader_order_kerne
         int idx[RS], tk[RS];
 #pragma unroll
         for (int i = 0; i < RS; ++i) {
-            idx[i] = (valid && i < len) ? p.set[q * S + i] : 0;
+            idx[i] = (valid && i < len) ? max(p.set[q * S + i], 0) : 0;
             tk[i] = (valid && i < len) ? p.ticket[q * S + i] : 0;
         }
         int perm[RS];
 #pragma unroll
         for (int i = 0; i < RS; ++i) perm[i] = i;
-
         bool pending = valid && len > 0;
         uint32_t spins = 0;
         while (__any_sync(KA_FULL, pending)) {
@@ -617,30 +841,7 @@ __global__ void __launch_bounds__(RS == 4 ? 1024 : 256, 1) ka_leader_order_kerne
                     }
                 }
                 if (ready) {
-                    // KAS:226-234: slot r takes, among the remaining brokers (ascending id), the one with the
-                    // least counter[.][r]; ties go to the earliest in the order rotated by |hash| % k (KAS:263-278).
-                    uint32_t remmask = (1u << len) - 1u;
-#pragma unroll
-                    for (int r = 0; r < RS; ++r) {
-                        if (r < len) {
-                            const int k = len - r;
-                            const int s = ka_rot_of<RS>(meta, k);
-                            long long best = 0x7FFFFFFFFFFFFFFFLL;
-                            int bpos = 0;
-#pragma unroll
-                            for (int pos = 0; pos < RS; ++pos) {
-                                if ((remmask >> pos) & 1u) {
-                                    int j = __popc(remmask & ((1u << pos) - 1u)) + s;
-                                    if (j >= k) j -= k;
-                                    const long long key = (long long)c[pos][r] * 8 + j;
-                                    if (key < best) { best = key; bpos = pos; }
-                                }
-                            }
-                            perm[r] = bpos;
-                            remmask &= ~(1u << bpos);
-                        }
-                    }
-                    // KAS:254-261: counter[list[r]][r] += 1 — one store per broker row commits the partition.
+                    ka_order_generic<RS>(c, len, meta, perm);
 #pragma unroll
                     for (int r = 0; r < RS; ++r) {
                         if (r < len) {
@@ -654,7 +855,7 @@ __global__ void __launch_bounds__(RS == 4 ? 1024 : 256, 1) ka_leader_order_kerne
                     pending = false;
                 }
             }
-            if (++spins > (1u << 24)) {  // guard: a ticket/set inconsistency must not hang the GPU
+            if (++spins > (1u << 22)) {
                 if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
                 pending = false;
             }

@@ -79,7 +79,7 @@ struct ka_ctx {
     float last_ms[8] = {};
     bool ev_valid = false;
     int64_t launches = 0;
-    int order_threads = 1024;  // leader-order CTA size (KA_ORDER_THREADS overrides; tuning knob)
+    int order_threads = 0;  // leader-order CTA size override (0 = heuristic from N); env KA_ORDER_THREADS wins
     // staged problem (between the context-free stage and the leader-order stage)
     bool staged = false;
     int64_t st_Q = 0;
@@ -321,13 +321,33 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         o.out = d_out;
         o.out_len = d_out_len;
         o.err_flag = c->d_flags.as<int>() + 1;
-        int nt = c->order_threads;
+        // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide, and every extra polling warp
+        // costs the frontier warps issue slots — measured best: 4 warps at N=100, 8 at N=1000, 32 at N=5000.
+        int nt = 128;
+        while (nt < 1024 && nt * 150 / 32 < N) nt *= 2;
+        if (c->order_threads > 0) nt = c->order_threads;
         if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
         o.sleep_ns = 48;
         o.near_dist = 1;
         if (const char* e = std::getenv("KA_ORDER_SLEEP_NS")) o.sleep_ns = (unsigned)std::atoi(e);
         if (const char* e = std::getenv("KA_ORDER_NEAR")) o.near_dist = std::atoi(e);
-        if (c->st_RS == 4) {
+        o.idle_polls = 4;
+        if (const char* e = std::getenv("KA_ORDER_IDLE")) o.idle_polls = (unsigned)std::atoi(e);
+        int spec = 1;
+        if (const char* e = std::getenv("KA_ORDER_SPEC")) spec = std::atoi(e);
+        if (c->st_RS == 4 && S <= 3 && spec) {
+#define KA_LAUNCH_ORDER3(NT)                                                        \
+    do {                                                                            \
+        KA_CUDA(allow_smem(ka_leader_order3_kernel<NT>, c->st_b_smem));             \
+        ka_leader_order3_kernel<NT><<<1, NT, c->st_b_smem, s>>>(o);                 \
+    } while (0)
+            if (nt >= 1024) KA_LAUNCH_ORDER3(1024);
+            else if (nt >= 512) KA_LAUNCH_ORDER3(512);
+            else if (nt >= 256) KA_LAUNCH_ORDER3(256);
+            else if (nt >= 128) KA_LAUNCH_ORDER3(128);
+            else KA_LAUNCH_ORDER3(64);
+#undef KA_LAUNCH_ORDER3
+        } else if (c->st_RS == 4) {
 #define KA_LAUNCH_ORDER4(NT)                                                        \
     do {                                                                            \
         KA_CUDA(allow_smem(ka_leader_order4_kernel<NT>, c->st_b_smem));             \

@@ -571,6 +571,7 @@ struct KaOrderParams {
     int* err_flag;            // set to KA_E_INTERNAL_SPIN if a window spins beyond the guard
     unsigned sleep_ns;        // back-off of warps with no partition near its turn (0 = spin)
     int near_dist;            // "near" = at most this many commits away on the slowest broker
+    unsigned idle_polls;      // speculative kernel: polls without any commit in the warp before it backs off
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -761,6 +762,135 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order4_kernel(const KaOrderPa
             if (S > 1) o[1] = len > 1 ? __ldg(&p.broker_id[i1]) : -1;
             if (S > 2) o[2] = len > 2 ? __ldg(&p.broker_id[i2]) : -1;
             if (S > 3) o[3] = len > 3 ? __ldg(&p.broker_id[i3]) : -1;
+            if (p.out_len) p.out_len[q] = len;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) p.ctr8[(i >> 2) * KA_MAX_SLOTS + (i & 3)] = ctr[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B, speculative straight-line variant for rows of <= 3 replicas (the RF=3 case of every BASELINE
+// config). Each poll iteration reads the three counter rows, evaluates readiness AND the ordering decision
+// side by side (independent instruction chains overlap inside the single warp), and commits with
+// predicated stores. No divergent "ready path": an iteration costs the same whether 0 or 32 lanes commit.
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderParams p) {
+    extern __shared__ __align__(16) unsigned char ka_smem[];
+    int* ctr = reinterpret_cast<int*>(ka_smem);  // [N][4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int S = p.S;  // <= 3
+
+    for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) ctr[i] = p.ctr8[(i >> 2) * KA_MAX_SLOTS + (i & 3)];
+    __syncthreads();
+
+    const int64_t nwin = (p.Q + 31) >> 5;
+    uint32_t n_meta = 0u;
+    int n_i0 = 0, n_i1 = 0, n_i2 = 0, n_t0 = 0, n_t1 = 0, n_t2 = 0;
+    auto fetch = [&](int64_t win) {
+        const int64_t q = win * 32 + lane;
+        n_meta = 0u;
+        if (win < nwin && q < p.Q) {
+            n_meta = __ldg(p.meta + q);
+            const int32_t* sp = p.set + q * S;
+            const int32_t* tp = p.ticket + q * S;
+            n_i0 = __ldg(sp); n_t0 = __ldg(tp);
+            if (S > 1) { n_i1 = __ldg(sp + 1); n_t1 = __ldg(tp + 1); }
+            if (S > 2) { n_i2 = __ldg(sp + 2); n_t2 = __ldg(tp + 2); }
+        }
+    };
+    fetch(warp);
+    const uint32_t cbase = ka_smem_u32(ctr);
+
+    for (int64_t win = warp; win < nwin; win += nwarp) {
+        const int64_t q = win * 32 + lane;
+        const bool valid = q < p.Q;
+        const uint32_t meta = n_meta;
+        const int len = (int)(meta & 15u);
+        // byte offsets of the broker rows; unused slots alias slot 0 so the readiness test stays uniform
+        const int o0 = (len > 0 ? max(n_i0, 0) : 0) * 16;
+        const int o1 = len > 1 ? max(n_i1, 0) * 16 : o0;
+        const int o2 = len > 2 ? max(n_i2, 0) * 16 : o0;
+        const int t0 = n_t0;
+        const int t1 = len > 1 ? n_t1 : t0, t2 = len > 2 ? n_t2 : t0;
+        fetch(win + nwarp);
+
+        const int s2 = (int)((meta >> 4) & 1u), s3 = (int)((meta >> 5) & 3u);
+        const int j0 = s3, j1 = (s3 + 1 >= 3) ? s3 - 2 : s3 + 1, j2 = (s3 + 2 >= 3) ? s3 - 1 : s3 + 2;
+        const int t10 = j1 < j0 ? 1 : 0, t20 = j2 < j0 ? 1 : 0, t21 = j2 < j1 ? 1 : 0;
+
+        bool pending = valid && len > 0;
+        // lanes with nothing to do poll one fixed row (a broadcast: one shared-memory wavefront)
+        uint32_t a0 = cbase + (pending ? o0 : 0), a1 = cbase + (pending ? o1 : 0), a2 = cbase + (pending ? o2 : 0);
+        int pb0 = 0, pb1 = 1, pb2 = 2;
+        uint32_t spins = 0, idle = 0;
+        for (;;) {
+            int4 r0, r1, r2;
+            asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
+            asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
+            asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r2.x), "=r"(r2.y), "=r"(r2.z), "=r"(r2.w) : "r"(a2));
+            // readiness: every broker row sums to this partition's ticket
+            const int e = (t0 - r0.x - r0.y - (r0.z + r0.w)) | (t1 - r1.x - r1.y - (r1.z + r1.w)) | (t2 - r2.x - r2.y - (r2.z + r2.w));
+            // speculative RF=3 decision (KAS:226-234; meaningful when e == 0 and len == 3)
+            const bool lt10 = r1.x < r0.x + t10;
+            const int m = lt10 ? 1 : 0;
+            const int cm = lt10 ? r1.x : r0.x;
+            const bool lt2m = r2.x < cm + (lt10 ? t21 : t20);
+            const int b0 = lt2m ? 2 : m;
+            const int v0 = lt2m ? r2.x : cm;
+            const int ca = (b0 == 0) ? r1.y : r0.y;
+            const int cbv = (b0 == 2) ? r1.y : r2.y;
+            const int pa = (b0 == 0) ? 1 : 0, pb = (b0 == 2) ? 1 : 2;
+            const bool pickb = s2 ? !(ca < cbv) : (cbv < ca);
+            const int b1 = pickb ? pb : pa;
+            const int v1 = pickb ? cbv : ca;
+            const int b2 = 3 - b0 - b1;
+            const uint32_t ad0 = (b0 == 0) ? a0 : ((b0 == 1) ? a1 : a2);
+            const uint32_t ad1 = (b1 == 0) ? a0 : ((b1 == 1) ? a1 : a2);
+            const uint32_t ad2 = (b2 == 0) ? a0 : ((b2 == 1) ? a1 : a2);
+            const int v2 = (b2 == 0) ? r0.z : ((b2 == 1) ? r1.z : r2.z);
+            const bool commit = pending && e == 0;
+            if (commit) {
+                if (len == 3) {
+                    // counter[list[r]][r] += 1 (KAS:254-261): one store per broker row commits the partition
+                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ad0), "r"(v0 + 1) : "memory");
+                    asm volatile("st.volatile.shared.s32 [%0+4], %1;" ::"r"(ad1), "r"(v1 + 1) : "memory");
+                    asm volatile("st.volatile.shared.s32 [%0+8], %1;" ::"r"(ad2), "r"(v2 + 1) : "memory");
+                    pb0 = b0; pb1 = b1; pb2 = b2;
+                } else if (len == 2) {
+                    // two replicas: slot 0 over {0,1} rotated by s2, slot 1 is the other
+                    const bool pick1 = s2 ? !(r0.x < r1.x) : (r1.x < r0.x);
+                    pb0 = pick1 ? 1 : 0; pb1 = 1 - pb0;
+                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pick1 ? a1 : a0), "r"((pick1 ? r1.x : r0.x) + 1) : "memory");
+                    asm volatile("st.volatile.shared.s32 [%0+4], %1;" ::"r"(pick1 ? a0 : a1), "r"((pick1 ? r0.y : r1.y) + 1) : "memory");
+                } else {
+                    pb0 = 0;
+                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a0), "r"(r0.x + 1) : "memory");
+                }
+                pending = false;
+                a0 = a1 = a2 = cbase;
+            }
+            const uint32_t cm_mask = __ballot_sync(KA_FULL, commit);
+            if (!__any_sync(KA_FULL, pending)) break;  // every lane of the window has committed
+            if (cm_mask) {
+                idle = 0;
+            } else if (++idle > p.idle_polls && p.sleep_ns > 0) {
+                // nothing in this warp moved for a while: it is waiting on warps at the frontier — yield the issue
+                // slots and the shared-memory port to them.
+                __nanosleep(p.sleep_ns);
+            }
+            if (++spins > (1u << 22)) {  // guard: a ticket/set inconsistency must not hang the GPU
+                if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
+                break;
+            }
+        }
+        if (valid) {
+            const int i0 = ka_sel4(pb0, o0, o1, o2, 0) >> 4, i1 = ka_sel4(pb1, o0, o1, o2, 0) >> 4, i2 = ka_sel4(pb2, o0, o1, o2, 0) >> 4;
+            int32_t* o = p.out + q * S;
+            o[0] = len > 0 ? __ldg(&p.broker_id[i0]) : -1;
+            if (S > 1) o[1] = len > 1 ? __ldg(&p.broker_id[i1]) : -1;
+            if (S > 2) o[2] = len > 2 ? __ldg(&p.broker_id[i2]) : -1;
             if (p.out_len) p.out_len[q] = len;
         }
     }

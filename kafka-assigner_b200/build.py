@@ -19,6 +19,23 @@ def _nvcc():
     raise RuntimeError("nvcc not found: libkassign.so cannot be built (there is no CPU fallback)")
 
 
+HOST_DIR = os.path.join(_HERE, "host")
+CLI = os.path.join(_HERE, "bin", "kafka-assignment-generator")
+HOST_SOURCES = ["kafka_assignment_generator.cpp", "kassign_host.hpp"]
+
+
+def build_host(force=False):
+    """g++ the C++ host mirror + file-based CLI (reference flag surface) against libkassign.so."""
+    deps = [os.path.join(HOST_DIR, f) for f in HOST_SOURCES] + [LIB, os.path.join(_HERE, "..", "include", "kassign.h")]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps if os.path.exists(d)):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", os.path.join(HOST_DIR, "kafka_assignment_generator.cpp"), "-L" + CSRC, "-lkassign",
+           "-Wl,-rpath,$ORIGIN/../csrc", "-o", CLI]
+    subprocess.check_call(cmd)
+    return CLI
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -321,10 +321,11 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         o.out = d_out;
         o.out_len = d_out_len;
         o.err_flag = c->d_flags.as<int>() + 1;
-        // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide, and every extra polling warp
-        // costs the frontier warps issue slots — measured best: 4 warps at N=100, 8 at N=1000, 32 at N=5000.
+        // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide and every extra polling warp costs
+        // the frontier warps issue slots and shared-memory bandwidth. Measured optimum (tools/phase_times.py):
+        // 128 threads at N=100, 512 at N=1000, 1024 at N=5000  ->  next power of two >= N/2, clamped.
         int nt = 128;
-        while (nt < 1024 && nt * 150 / 32 < N) nt *= 2;
+        while (nt < 1024 && nt * 2 < N) nt *= 2;
         if (c->order_threads > 0) nt = c->order_threads;
         if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
         o.sleep_ns = 48;

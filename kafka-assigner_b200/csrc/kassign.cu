@@ -67,6 +67,7 @@ struct ka_ctx {
     uint32_t range = 0;
     int blob_bytes = 16;
     int lut_off = 0;
+    int R = 0, roff_off = 0, memb_off = 0;
     DevBuf d_blob, d_glut, d_broker_id, d_ctr8;
     // counters of brokers not in the current table (Context.counter is keyed by broker id)
     std::unordered_map<int32_t, std::vector<int32_t>> parked;
@@ -138,6 +139,7 @@ int park_counters(ka_ctx* c) {
 struct Plan {
     // kernel A
     int a_warps, a_grid, a_load_bytes, a_slab_bytes, a_cnt_bytes, a_load_kind;  // kind 0=u8 1=u16 2=u32
+    int a_rackptr, a_rp_bytes;
     size_t a_smem;
     // tickets
     int64_t L;
@@ -157,7 +159,13 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, Plan& pl, k
     pl.a_load_bytes = (int)align16((size_t)std::max(N, 1) * lsz);
     pl.a_slab_bytes = (int)align16((size_t)std::max(Pmax, 1) * S * 2);
     pl.a_cnt_bytes = (int)align16((size_t)std::max(Pmax, 1));
-    const size_t per_warp = (size_t)pl.a_load_bytes + pl.a_slab_bytes + pl.a_cnt_bytes;
+    // spread phase: window scan over the rotated order by default (measured faster on every BASELINE config: the
+    // monotone head finds a slot within ~1 window); KA_SPREAD_RACKPTR=1 selects the per-rack first-free-pointer
+    // variant (exact too; pays off only when walks are long: many full nodes AND tight rack constraints).
+    pl.a_rackptr = 0;
+    if (const char* e = std::getenv("KA_SPREAD_RACKPTR")) pl.a_rackptr = std::atoi(e) && c->R > 0 && c->R <= 4096;
+    pl.a_rp_bytes = pl.a_rackptr ? (int)align16((size_t)c->R * 2) : 0;
+    const size_t per_warp = (size_t)pl.a_load_bytes + pl.a_slab_bytes + pl.a_cnt_bytes + 3 * (size_t)pl.a_rp_bytes;
     const size_t shared = 16 + (size_t)c->blob_bytes;
     if (shared + per_warp > KA_SMEM_BUDGET) return set_status(st, KA_ERR_LIMIT, -1, -1, Pmax, N);
     pl.a_warps = (int)std::min<size_t>(16, (KA_SMEM_BUDGET - shared) / per_warp);
@@ -233,6 +241,11 @@ int enqueue_stage(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const
         p.blob = c->d_blob.as<uint16_t>();
         p.blob_bytes = c->blob_bytes;
         p.lut_off = c->lut_off;
+        p.R = c->R;
+        p.rackptr = pl.a_rackptr;
+        p.roff_off = c->roff_off;
+        p.memb_off = c->memb_off;
+        p.rp_bytes = pl.a_rp_bytes;
         p.lut_mode = c->lut_mode;
         p.min_id = c->min_id;
         p.range = c->range;
@@ -526,32 +539,50 @@ int32_t ka_ctx_set_brokers(ka_ctx* c, int32_t N, const int32_t* broker_id, const
     c->min_id = N > 0 ? broker_id[0] : 0;
     const uint64_t range64 = N > 0 ? (uint64_t)((int64_t)broker_id[N - 1] - (int64_t)broker_id[0]) + 1 : 0;
     const size_t npad = align16((size_t)std::max(N, 1) * 2) / 2;  // uint16 elements, 16B multiple
+    // compact rack ids in order of first appearance (rack identity is all that matters, KAS:90-94)
+    std::vector<uint16_t> rackc(std::max(N, 1), 0);
+    {
+        std::unordered_map<int32_t, int> seen;
+        for (int i = 0; i < N; ++i) {
+            auto it = seen.find(broker_rack[i]);
+            if (it == seen.end()) it = seen.emplace(broker_rack[i], (int)seen.size()).first;
+            rackc[i] = (uint16_t)it->second;
+        }
+        c->R = (int)seen.size();
+    }
     std::vector<uint16_t> blob;
+    size_t lut_elems = 0;
     if (range64 <= KA_LUT_SMEM_MAX_RANGE) {
         c->lut_mode = KA_LUT_SMEM;
         c->range = (uint32_t)range64;
-        const size_t rpad = align16((size_t)std::max<uint64_t>(range64, 1) * 2) / 2;
-        blob.assign(npad + rpad, (uint16_t)KA_DEAD);
-        for (int i = 0; i < N; ++i) {
-            blob[i] = (uint16_t)broker_rack[i];
-            blob[npad + (size_t)((int64_t)broker_id[i] - c->min_id)] = (uint16_t)i;
-        }
-        c->lut_off = (int)npad;
+        lut_elems = align16((size_t)std::max<uint64_t>(range64, 1) * 2) / 2;
+    } else if (range64 <= KA_LUT_GLOBAL_MAX_RANGE) {
+        c->lut_mode = KA_LUT_GLOBAL;
+        c->range = (uint32_t)range64;
+        std::vector<uint16_t> g((size_t)range64, (uint16_t)KA_DEAD);
+        for (int i = 0; i < N; ++i) g[(size_t)((int64_t)broker_id[i] - c->min_id)] = (uint16_t)i;
+        KA_CUDA(c->d_glut.reserve(g.size() * 2));
+        KA_CUDA(cudaMemcpy(c->d_glut.p, g.data(), g.size() * 2, cudaMemcpyHostToDevice));
     } else {
-        blob.assign(npad, (uint16_t)KA_DEAD);
-        for (int i = 0; i < N; ++i) blob[i] = (uint16_t)broker_rack[i];
-        c->lut_off = 0;
-        if (range64 <= KA_LUT_GLOBAL_MAX_RANGE) {
-            c->lut_mode = KA_LUT_GLOBAL;
-            c->range = (uint32_t)range64;
-            std::vector<uint16_t> g((size_t)range64, (uint16_t)KA_DEAD);
-            for (int i = 0; i < N; ++i) g[(size_t)((int64_t)broker_id[i] - c->min_id)] = (uint16_t)i;
-            KA_CUDA(c->d_glut.reserve(g.size() * 2));
-            KA_CUDA(cudaMemcpy(c->d_glut.p, g.data(), g.size() * 2, cudaMemcpyHostToDevice));
-        } else {
-            c->lut_mode = KA_LUT_BSEARCH;
-            c->range = 0;
-        }
+        c->lut_mode = KA_LUT_BSEARCH;
+        c->range = 0;
+    }
+    const size_t roff_elems = align16((size_t)(c->R + 1) * 2) / 2;
+    c->lut_off = (int)npad;
+    c->roff_off = (int)(npad + lut_elems);
+    c->memb_off = (int)(npad + lut_elems + roff_elems);
+    blob.assign(npad + lut_elems + roff_elems + npad, (uint16_t)KA_DEAD);
+    for (int i = 0; i < N; ++i) {
+        blob[i] = rackc[i];
+        if (c->lut_mode == KA_LUT_SMEM) blob[npad + (size_t)((int64_t)broker_id[i] - c->min_id)] = (uint16_t)i;
+    }
+    {   // rack member lists (CSR): sorted indices ascending inside each rack
+        std::vector<int> cntr(c->R + 1, 0);
+        for (int i = 0; i < N; ++i) cntr[rackc[i] + 1]++;
+        for (int r = 0; r < c->R; ++r) cntr[r + 1] += cntr[r];
+        for (int r = 0; r <= c->R; ++r) blob[c->roff_off + r] = (uint16_t)cntr[r];
+        std::vector<int> fill(cntr.begin(), cntr.end() - 1);
+        for (int i = 0; i < N; ++i) blob[c->memb_off + fill[rackc[i]]++] = (uint16_t)i;
     }
     c->blob_bytes = (int)(blob.size() * 2);
     KA_CUDA(c->d_blob.reserve(blob.size() * 2));

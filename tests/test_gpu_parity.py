@@ -2,6 +2,7 @@
 (all arithmetic on this path is integer). Mirrors the reference's own tests
 (KafkaTopicAssignerTest.java:18-157) through the host-side KafkaTopicAssigner mirror, then the golden
 fixtures, seeded random clusters, the BASELINE configs and size-independent properties at full size."""
+import os
 import random
 
 import numpy as np
@@ -277,3 +278,105 @@ def test_stage_order_split_and_counter_ring_on_one_gpu(native_lib, oracle):
         torch.cuda.synchronize()
         outs.append(do.cpu().numpy().reshape(-1, 3))
     assert np.array_equal(np.concatenate(outs), exp)
+
+
+@pytest.mark.parametrize("frac", [0.01, 0.2, 0.5])
+def test_baseline_config5_decommission_prefix(native_lib, oracle, frac):
+    """BASELINE config 5 shape (10k brokers / 50 racks, 1000-partition topics), a topic prefix, brokers removed."""
+    cl = kab.synth.make_config("c5", "mixed", remove_frac=frac, T=24)
+    exp_out, _, est = util.oracle_dense(oracle, cl)
+    out, _, st = kab.Solver(0).solve_cluster(cl, check=False)
+    assert st.code == est.code == 0
+    assert np.array_equal(out.reshape(-1, 3), exp_out)
+    assert not np.isin(out, np.setdiff1d(1000 + np.arange(10000), cl.broker_id)).any()
+
+
+# ---- less-travelled code paths ----------------------------------------------------------------------------------------
+def _random_case(rng, broker_ids, n_topics, max_rf, max_parts=40, rack_groups=None, desired=-1):
+    racks = {}
+    if rack_groups:
+        for b in broker_ids:
+            if rng.random() < 0.85:
+                racks[b] = "g%d" % rng.randrange(rack_groups)
+    topics = []
+    universe = list(broker_ids) + [broker_ids[0] - 7, broker_ids[-1] + 11]
+    for ti in range(n_topics):
+        rf = rng.randint(1, min(max_rf, len(broker_ids)))
+        cur = {p: rng.sample(universe, min(rf, len(universe))) for p in sorted(rng.sample(range(0, 200), rng.randint(1, max_parts)))}
+        topics.append(("lt%d" % ti, cur))
+    return dict(topics=topics, brokers=list(broker_ids), racks=racks, desired_rf=desired)
+
+
+def test_broker_id_lookup_modes(native_lib, oracle):
+    """id -> index lookup: smem LUT (dense ids), global LUT (range > 32768), binary search (range > 2^25)."""
+    rng = random.Random(5)
+    dense = sorted(rng.sample(range(100, 400), 60))
+    wide = sorted(rng.sample(range(-40000, 40000), 60))                 # range ~80k  -> global LUT
+    huge = sorted(rng.sample(range(-2**31 + 5, 2**31 - 5), 60))        # range ~4e9  -> binary search
+    for ids in (dense, wide, huge):
+        for it in range(6):
+            case = _random_case(rng, ids, n_topics=4, max_rf=4, rack_groups=rng.choice([None, 7, 20]))
+            exp = util.run_oracle_case(oracle, case)
+            got = util.run_gpu_case(kab, case)
+            assert got == exp, (ids[:3], it)
+
+
+def test_wide_rows_five_to_eight_replicas(native_lib, oracle):
+    """Lists of 5..8 replicas use the generic 8-slot leader-order kernel."""
+    rng = random.Random(8)
+    ids = list(range(1, 41))
+    n_ok = 0
+    for it in range(12):
+        case = _random_case(rng, ids, n_topics=3, max_rf=8, max_parts=25, rack_groups=rng.choice([None, 12, 40]))
+        exp = util.run_oracle_case(oracle, case)
+        got = util.run_gpu_case(kab, case)
+        assert got == exp, it
+        n_ok += "records" in exp
+    assert n_ok >= 3
+    # replication-factor growth to 6 via --desired_replication_factor
+    case = _random_case(rng, ids, n_topics=3, max_rf=3, max_parts=20, rack_groups=None, desired=6)
+    assert util.run_gpu_case(kab, case) == util.run_oracle_case(oracle, case)
+
+
+def test_degenerate_shapes(native_lib, oracle):
+    s = kab.Solver(0)
+    # zero topics
+    s.set_brokers(np.array([1, 2, 3], dtype=np.int32), np.array([0, 1, 2], dtype=np.int32))
+    out, out_len, st = s.solve_dense(np.zeros(0, dtype=np.int32), np.zeros((0, 4, 2), dtype=np.int32))
+    assert st.code == 0 and out.shape == (0, 4, 2)
+    # single broker, RF 1
+    case = dict(topics=[("solo", {0: [9], 1: [9], 5: [4]})], brokers=[9], racks={}, desired_rf=-1)
+    assert util.run_gpu_case(kab, case) == util.run_oracle_case(oracle, case)
+    # topic with an empty partition map between two good topics: fails at that topic (KTA:65-66)
+    case = dict(topics=[("a", {0: [1, 2]}), ("empty", {}), ("b", {0: [2, 3]})], brokers=[1, 2, 3], racks={}, desired_rf=-1)
+    got, exp = util.run_gpu_case(kab, case), util.run_oracle_case(oracle, case)
+    assert got == exp and exp["topic_index"] == 1
+    # ... but with a desired RF an empty topic is fine and yields no rows
+    case["desired_rf"] = 2
+    assert util.run_gpu_case(kab, case) == util.run_oracle_case(oracle, case)
+    # every current broker dead: everything is an orphan
+    case = dict(topics=[("dead", {p: [100 + p, 200 + p] for p in range(6)})], brokers=[1, 2, 3, 4], racks={1: "x", 2: "y"}, desired_rf=-1)
+    assert util.run_gpu_case(kab, case) == util.run_oracle_case(oracle, case)
+    # duplicate broker inside a current list (second copy is dropped, KAS:320-324)
+    case = dict(topics=[("dup", {0: [1, 1], 1: [2, 2], 2: [1, 2]})], brokers=[1, 2, 3], racks={}, desired_rf=-1)
+    assert util.run_gpu_case(kab, case) == util.run_oracle_case(oracle, case)
+    # limits are reported, not silently mishandled
+    with pytest.raises(kab.KassignError):
+        kab.KafkaTopicAssigner().generate_assignment("big", {0: list(range(1, 10))}, set(range(1, 12)), {}, -1)  # 9 replicas > 8 slots
+
+
+def test_rack_pointer_spread_variant_is_exact(native_lib, oracle):
+    """The opt-in per-rack-pointer spread (KA_SPREAD_RACKPTR=1) must give the same bytes as the default window scan."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, kafka_assigner_b200 as kab\n"
+            "for key, kind in (('c1','random'), ('c2','mixed')):\n"
+            "    cl = kab.synth.make_config(key, kind)\n"
+            "    out, _, st = kab.Solver(0).solve_cluster(cl)\n"
+            "    np.save('/tmp/_rp_%s.npy' % key, out)\n")
+    env = dict(os.environ, KA_SPREAD_RACKPTR="1", PYTHONPATH=util.os.path.dirname(util.HERE))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    for key, kind in (("c1", "random"), ("c2", "mixed")):
+        cl = kab.synth.make_config(key, kind)
+        exp, _, _ = util.oracle_dense(oracle, cl)
+        assert np.array_equal(np.load("/tmp/_rp_%s.npy" % key).reshape(-1, 3), exp)

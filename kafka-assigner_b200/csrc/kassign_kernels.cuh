@@ -946,32 +946,32 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
                 asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
                 asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r2.x), "=r"(r2.y), "=r"(r2.z), "=r"(r2.w) : "r"(a2));
                 const int e = (t0 - r0.x - r0.y - (r0.z + r0.w)) | (t1 - r1.x - r1.y - (r1.z + r1.w)) | (t2 - r2.x - r2.y - (r2.z + r2.w));
+                const bool commit = pending && e == 0;
                 // slot 0 (leader): pairwise "beats" among the three counters, then combine
                 const bool L10 = r1.x < r0.x + t10, L20 = r2.x < r0.x + t20, L21 = r2.x < r1.x + t21;
                 const bool is2 = L10 ? L21 : L20;           // position 2 wins
                 const bool is1 = L10 && !L21;               // position 1 wins
                 const int b0 = is2 ? 2 : (is1 ? 1 : 0);
+                const int v0 = is2 ? r2.x : (is1 ? r1.x : r0.x);
+                const uint32_t ad0 = is2 ? a2 : (is1 ? a1 : a0);
+                // counter[list[r]][r] += 1 (KAS:254-261): one store per broker row; each store is issued as soon as
+                // its operands exist so the next partition on that broker wakes up as early as possible
+                if (commit) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ad0), "r"(v0 + 1) : "memory");
                 // slot 1: for each possible remaining pair (lo, hi): does hi get picked? (rotation s2 = who is scanned first)
-                const bool P01 = s2 ? !(r0.y < r1.y) : (r1.y < r0.y);
-                const bool P02 = s2 ? !(r0.y < r2.y) : (r2.y < r0.y);
-                const bool P12 = s2 ? !(r1.y < r2.y) : (r2.y < r1.y);
+                const bool P01 = r1.y < r0.y + s2, P02 = r2.y < r0.y + s2, P12 = r2.y < r1.y + s2;
                 const bool pickhi = is2 ? P01 : (is1 ? P02 : P12);
                 // remaining pair: b0==0 -> (1,2), b0==1 -> (0,2), b0==2 -> (0,1)
                 const int lo = (b0 == 0) ? 1 : 0, hi = is2 ? 1 : 2;
                 const int b1 = pickhi ? hi : lo;
-                const int v0 = is2 ? r2.x : (is1 ? r1.x : r0.x);
                 const int ylo = (b0 == 0) ? r1.y : r0.y, yhi = is2 ? r1.y : r2.y;
                 const int v1 = pickhi ? yhi : ylo;
                 const uint32_t alo = (b0 == 0) ? a1 : a0, ahi = is2 ? a1 : a2;
-                const int zlo = (b0 == 0) ? r1.z : r0.z, zhi = is2 ? r1.z : r2.z;
-                const uint32_t ad0 = is2 ? a2 : (is1 ? a1 : a0);
                 const uint32_t ad1 = pickhi ? ahi : alo;
+                if (commit) asm volatile("st.volatile.shared.s32 [%0+4], %1;" ::"r"(ad1), "r"(v1 + 1) : "memory");
+                const int zlo = (b0 == 0) ? r1.z : r0.z, zhi = is2 ? r1.z : r2.z;
                 const uint32_t ad2 = pickhi ? alo : ahi;
                 const int v2 = pickhi ? zlo : zhi;
-                if (pending && e == 0) {
-                    // counter[list[r]][r] += 1 (KAS:254-261): one store per broker row commits the partition
-                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ad0), "r"(v0 + 1) : "memory");
-                    asm volatile("st.volatile.shared.s32 [%0+4], %1;" ::"r"(ad1), "r"(v1 + 1) : "memory");
+                if (commit) {
                     asm volatile("st.volatile.shared.s32 [%0+8], %1;" ::"r"(ad2), "r"(v2 + 1) : "memory");
                     pcode = b0 | (b1 << 2);
                     pending = false;

@@ -73,6 +73,7 @@ struct ka_ctx {
     std::unordered_map<int32_t, std::vector<int32_t>> parked;
     // scratch
     DevBuf d_hash, d_part_off, d_rep_off, d_cur, d_set, d_meta, d_ticket, d_out, d_out_len, d_hist, d_tstatus, d_flags;
+    DevBuf d_tick4, d_idx01, d_pcode;
     HostPinned* h_pin = nullptr;
     // bookkeeping
     bool timing = false;
@@ -310,12 +311,21 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
     const int N = c->N, S = c->st_S;
     const int64_t Q = c->st_Q;
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[7], s));
+    int spec = 1;
+    if (const char* e = std::getenv("KA_ORDER_SPEC")) spec = std::atoi(e);
+    const bool packed = c->st_RS == 4 && S <= 3 && spec;  // rows of <= 3 replicas: packed records + emit kernel
     if (Q > 0 && N > 0) {
         KA_CUDA(allow_smem(ka_ticket_rank_kernel, c->st_rank_smem));
+        if (packed) {
+            KA_CUDA(c->d_tick4.reserve((size_t)Q * 16));
+            KA_CUDA(c->d_idx01.reserve((size_t)Q * 4));
+            KA_CUDA(c->d_pcode.reserve((size_t)Q));
+        }
         ka_ticket_scan_kernel<<<(N + 255) / 256, 256, 0, s>>>(c->d_hist.as<int32_t>(), c->st_chunks, N, c->d_ctr8.as<int32_t>(), c->st_RS);
         KA_CUDA(cudaGetLastError());
         ka_ticket_rank_kernel<<<c->st_rank_grid, c->st_rank_warps * 32, c->st_rank_smem, s>>>(
-            c->d_set.as<int32_t>(), Q, S, N, c->st_L, c->st_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>());
+            c->d_set.as<int32_t>(), Q, S, N, c->st_L, c->st_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>(),
+            c->d_meta.as<uint32_t>(), packed ? c->d_tick4.as<int4>() : nullptr, packed ? c->d_idx01.as<uint32_t>() : nullptr);
         KA_CUDA(cudaGetLastError());
         c->launches += 2;
     }
@@ -334,22 +344,26 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         o.out = d_out;
         o.out_len = d_out_len;
         o.err_flag = c->d_flags.as<int>() + 1;
-        // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide and every extra polling warp costs
-        // the frontier warps issue slots and shared-memory bandwidth. Measured optimum (tools/phase_times.py):
-        // 128 threads at N=100, 512 at N=1000, 1024 at N=5000  ->  next power of two >= N/2, clamped.
-        int nt = 128;
-        while (nt < 1024 && nt * 2 < N) nt *= 2;
+        // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide and every extra polling warp costs the
+        // frontier warps issue slots. Measured optimum (tools/phase_times.py, packed-record kernel): 128 threads at
+        // N=100, 256 at N=1000, 512 at N=5000, 1024 at N=10000.
+        int nt = N < 400 ? 128 : (N < 2500 ? 256 : (N < 7500 ? 512 : 1024));
         if (c->order_threads > 0) nt = c->order_threads;
         if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
-        o.sleep_ns = 48;
+        o.sleep_ns = 0;
         o.near_dist = 1;
         if (const char* e = std::getenv("KA_ORDER_SLEEP_NS")) o.sleep_ns = (unsigned)std::atoi(e);
         if (const char* e = std::getenv("KA_ORDER_NEAR")) o.near_dist = std::atoi(e);
         o.idle_polls = 4;
         if (const char* e = std::getenv("KA_ORDER_IDLE")) o.idle_polls = (unsigned)std::atoi(e);
-        int spec = 1;
-        if (const char* e = std::getenv("KA_ORDER_SPEC")) spec = std::atoi(e);
-        if (c->st_RS == 4 && S <= 3 && spec) {
+        o.wide = 0;  // measured slower on every BASELINE config; kept as an experiment knob (KA_ORDER_WIDE=1)
+        o.skip_shift = 0;
+        if (const char* e = std::getenv("KA_ORDER_WIDE")) o.wide = std::atoi(e);
+        if (const char* e = std::getenv("KA_ORDER_SKIP_SHIFT")) o.skip_shift = std::atoi(e);
+        o.tick4 = c->d_tick4.as<int4>();
+        o.idx01 = c->d_idx01.as<uint32_t>();
+        o.pcode = c->d_pcode.as<uint8_t>();
+        if (packed) {
 #define KA_LAUNCH_ORDER3(NT)                                                        \
     do {                                                                            \
         KA_CUDA(allow_smem(ka_leader_order3_kernel<NT>, c->st_b_smem));             \
@@ -378,6 +392,12 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         }
         KA_CUDA(cudaGetLastError());
         c->launches++;
+        if (packed) {
+            ka_emit_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(c->d_set.as<int32_t>(), c->d_meta.as<uint32_t>(), c->d_pcode.as<uint8_t>(),
+                                                                     c->d_broker_id.as<int32_t>(), Q, S, d_out, d_out_len);
+            KA_CUDA(cudaGetLastError());
+            c->launches++;
+        }
     }
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
     c->staged = false;
@@ -503,7 +523,7 @@ void ka_ctx_destroy(ka_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_blob, &c->d_glut, &c->d_broker_id, &c->d_ctr8, &c->d_hash, &c->d_part_off, &c->d_rep_off, &c->d_cur, &c->d_set,
-                      &c->d_meta, &c->d_ticket, &c->d_out, &c->d_out_len, &c->d_hist, &c->d_tstatus, &c->d_flags})
+                      &c->d_meta, &c->d_ticket, &c->d_tick4, &c->d_idx01, &c->d_pcode, &c->d_out, &c->d_out_len, &c->d_hist, &c->d_tstatus, &c->d_flags})
         b->release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);

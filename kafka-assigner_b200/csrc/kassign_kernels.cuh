@@ -611,9 +611,13 @@ __global__ void ka_ticket_scan_kernel(int32_t* hist, int num_chunks, int N, cons
     }
 }
 
+// When tick4/idx01 are given (rows of <= 3 replicas) the pass also emits the packed per-partition record kernel B
+// consumes with one 128-bit and one 32-bit load:  tick4[q] = {t0, t1, t2, idx2 | (meta & 0xFFFF) << 16},
+// idx01[q] = idx0 | idx1 << 16.
 __global__ void __launch_bounds__(1024) ka_ticket_rank_kernel(const int32_t* __restrict__ set, int64_t Q, int S, int N, int64_t L,
                                                               int num_chunks, const int32_t* __restrict__ base,
-                                                              int32_t* __restrict__ ticket) {
+                                                              int32_t* __restrict__ ticket, const uint32_t* __restrict__ meta,
+                                                              int4* __restrict__ tick4, uint32_t* __restrict__ idx01) {
     extern __shared__ __align__(16) unsigned char ka_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const uint32_t lt = ka_lanemask_lt();
@@ -635,15 +639,21 @@ __global__ void __launch_bounds__(1024) ka_ticket_rank_kernel(const int32_t* __r
                 if (idx[i] >= 0) atomicOr(&owner[idx[i]], 1u << lane);
             __syncwarp();
             uint32_t own[KA_MAX_SLOTS];
+            int tkv[KA_MAX_SLOTS];
 #pragma unroll
             for (int i = 0; i < KA_MAX_SLOTS; ++i) {
                 own[i] = 0u;
+                tkv[i] = 0;
                 if (idx[i] >= 0) {
                     own[i] = owner[idx[i]];
-                    ticket[q * S + i] = issued[idx[i]] + __popc(own[i] & lt);
-                } else if (valid && i < S) {
-                    ticket[q * S + i] = 0;
+                    tkv[i] = issued[idx[i]] + __popc(own[i] & lt);
                 }
+                if (!tick4 && valid && i < S) ticket[q * S + i] = tkv[i];
+            }
+            if (tick4 && valid) {
+                const uint32_t m = meta[q];
+                tick4[q] = make_int4(tkv[0], tkv[1], tkv[2], (int)(((uint32_t)max(idx[2], 0) & 0xFFFFu) | ((m & 0xFFFFu) << 16)));
+                idx01[q] = ((uint32_t)max(idx[0], 0) & 0xFFFFu) | (((uint32_t)max(idx[1], 0) & 0xFFFFu) << 16);
             }
             __syncwarp();
 #pragma unroll
@@ -679,6 +689,11 @@ struct KaOrderParams {
     unsigned sleep_ns;        // back-off of warps with no partition near its turn (0 = spin)
     int near_dist;            // "near" = at most this many commits away on the slowest broker
     unsigned idle_polls;      // speculative kernel: polls without any commit in the warp before it backs off
+    const int4* tick4;        // order3: packed records from ka_ticket_rank_kernel
+    const uint32_t* idx01;
+    uint8_t* pcode;           // order3: chosen positions (b0 | b1 << 2) per partition, consumed by ka_emit_kernel
+    int wide;                 // RF=3 tight loop: 1 = skip polling while >= 2 commits away (many-warp CTAs)
+    int skip_shift;           // wide: iterations skipped = (distance - 1) >> skip_shift
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -882,29 +897,80 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order4_kernel(const KaOrderPa
 // side by side (independent instruction chains overlap inside the single warp), and commits with
 // predicated stores. No divergent "ready path": an iteration costs the same whether 0 or 32 lanes commit.
 // ------------------------------------------------------------------------------------------------
+// Tight RF=3 loop, "wide" flavour for CTAs with many polling warps (N in the thousands): the loop is then bound by
+// shared-memory bank conflicts of the random 16-byte row reads, not by latency. A lane whose slowest broker is still
+// d >= 2 commits away cannot become ready before d-1 more levels, so it stops polling for (d-1) >> skip_shift
+// iterations (predicated-off loads touch no bank), and a warp in which nobody polls skips the body altogether.
+__device__ __forceinline__ int ka_order3_window_wide(uint32_t a0, uint32_t a1, uint32_t a2, int t0, int t1, int t2, int t10, int t20,
+                                                     int t21, int s2, bool& pending, int skip_shift) {
+    int pcode = 0 | (1 << 2);
+    int skip = 0;
+    uint32_t spins = 0;
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0;
+    do {
+        const bool poll = pending && skip == 0;
+        if (__any_sync(KA_FULL, poll)) {
+            const int pp = poll ? 1 : 0;
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
+                         : "+r"(r0.x), "+r"(r0.y), "+r"(r0.z), "+r"(r0.w) : "r"(a0), "r"(pp));
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
+                         : "+r"(r1.x), "+r"(r1.y), "+r"(r1.z), "+r"(r1.w) : "r"(a1), "r"(pp));
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
+                         : "+r"(r2.x), "+r"(r2.y), "+r"(r2.z), "+r"(r2.w) : "r"(a2), "r"(pp));
+            const int e0 = t0 - r0.x - r0.y - (r0.z + r0.w), e1 = t1 - r1.x - r1.y - (r1.z + r1.w), e2 = t2 - r2.x - r2.y - (r2.z + r2.w);
+            const bool commit = poll && (e0 | e1 | e2) == 0;
+            const bool L10 = r1.x < r0.x + t10, L20 = r2.x < r0.x + t20, L21 = r2.x < r1.x + t21;
+            const bool is2 = L10 ? L21 : L20;
+            const bool is1 = L10 && !L21;
+            const int b0 = is2 ? 2 : (is1 ? 1 : 0);
+            const int v0 = is2 ? r2.x : (is1 ? r1.x : r0.x);
+            const uint32_t ad0 = is2 ? a2 : (is1 ? a1 : a0);
+            if (commit) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ad0), "r"(v0 + 1) : "memory");
+            const bool P01 = r1.y < r0.y + s2, P02 = r2.y < r0.y + s2, P12 = r2.y < r1.y + s2;
+            const bool pickhi = is2 ? P01 : (is1 ? P02 : P12);
+            const int lo = (b0 == 0) ? 1 : 0, hi = is2 ? 1 : 2;
+            const int b1 = pickhi ? hi : lo;
+            const int ylo = (b0 == 0) ? r1.y : r0.y, yhi = is2 ? r1.y : r2.y;
+            const int v1 = pickhi ? yhi : ylo;
+            const uint32_t alo = (b0 == 0) ? a1 : a0, ahi = is2 ? a1 : a2;
+            const uint32_t ad1 = pickhi ? ahi : alo;
+            if (commit) asm volatile("st.volatile.shared.s32 [%0+4], %1;" ::"r"(ad1), "r"(v1 + 1) : "memory");
+            const int zlo = (b0 == 0) ? r1.z : r0.z, zhi = is2 ? r1.z : r2.z;
+            const uint32_t ad2 = pickhi ? alo : ahi;
+            const int v2 = pickhi ? zlo : zhi;
+            if (commit) {
+                asm volatile("st.volatile.shared.s32 [%0+8], %1;" ::"r"(ad2), "r"(v2 + 1) : "memory");
+                pcode = b0 | (b1 << 2);
+                pending = false;
+            } else if (poll) {
+                skip = (max(e0, max(e1, e2)) - 1) >> skip_shift;  // distance 1 -> keep polling every iteration
+            }
+        }
+        if (!poll) skip -= (skip > 0);
+    } while (__any_sync(KA_FULL, pending) && ++spins < (1u << 22));
+    return pcode;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderParams p) {
     extern __shared__ __align__(16) unsigned char ka_smem[];
     int* ctr = reinterpret_cast<int*>(ka_smem);  // [N][4]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int S = p.S;  // <= 3
 
     for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) ctr[i] = p.ctr8[(i >> 2) * KA_MAX_SLOTS + (i & 3)];
     __syncthreads();
 
     const int64_t nwin = (p.Q + 31) >> 5;
-    uint32_t n_meta = 0u;
-    int n_i0 = 0, n_i1 = 0, n_i2 = 0, n_t0 = 0, n_t1 = 0, n_t2 = 0;
+    // software prefetch of the next window's packed records: global latency stays off the dependency chain
+    int4 n_tk = make_int4(0, 0, 0, 0);
+    uint32_t n_i01 = 0u;
     auto fetch = [&](int64_t win) {
         const int64_t q = win * 32 + lane;
-        n_meta = 0u;
+        n_tk = make_int4(0, 0, 0, 0);
+        n_i01 = 0u;
         if (win < nwin && q < p.Q) {
-            n_meta = __ldg(p.meta + q);
-            const int32_t* sp = p.set + q * S;
-            const int32_t* tp = p.ticket + q * S;
-            n_i0 = __ldg(sp); n_t0 = __ldg(tp);
-            if (S > 1) { n_i1 = __ldg(sp + 1); n_t1 = __ldg(tp + 1); }
-            if (S > 2) { n_i2 = __ldg(sp + 2); n_t2 = __ldg(tp + 2); }
+            n_tk = __ldg(p.tick4 + q);
+            n_i01 = __ldg(p.idx01 + q);
         }
     };
     fetch(warp);
@@ -913,14 +979,14 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
     for (int64_t win = warp; win < nwin; win += nwarp) {
         const int64_t q = win * 32 + lane;
         const bool valid = q < p.Q;
-        const uint32_t meta = n_meta;
+        const uint32_t meta = (uint32_t)n_tk.w >> 16;
         const int len = (int)(meta & 15u);
         // byte offsets of the broker rows; unused slots alias slot 0 so the readiness test stays uniform
-        const int o0 = (len > 0 ? max(n_i0, 0) : 0) * 16;
-        const int o1 = len > 1 ? max(n_i1, 0) * 16 : o0;
-        const int o2 = len > 2 ? max(n_i2, 0) * 16 : o0;
-        const int t0 = n_t0;
-        const int t1 = len > 1 ? n_t1 : t0, t2 = len > 2 ? n_t2 : t0;
+        const int o0 = (int)(n_i01 & 0xFFFFu) * 16;
+        const int o1 = len > 1 ? (int)(n_i01 >> 16) * 16 : o0;
+        const int o2 = len > 2 ? (int)((uint32_t)n_tk.w & 0xFFFFu) * 16 : o0;
+        const int t0 = n_tk.x;
+        const int t1 = len > 1 ? n_tk.y : t0, t2 = len > 2 ? n_tk.z : t0;
         fetch(win + nwarp);
 
         const int s2 = (int)((meta >> 4) & 1u), s3 = (int)((meta >> 5) & 3u);
@@ -933,7 +999,11 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
         int pb0 = 0, pb1 = 1, pb2 = 2;
         uint32_t spins = 0;
         const bool all3 = !__any_sync(KA_FULL, pending && len != 3);
-        if (all3) {
+        if (all3 && p.wide) {
+            const int pcode = ka_order3_window_wide(a0, a1, a2, t0, t1, t2, t10, t20, t21, s2, pending, p.skip_shift);
+            if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
+            pb0 = pcode & 3; pb1 = pcode >> 2; pb2 = 3 - pb0 - pb1;
+        } else if (all3) {
             // ---- tight loop: every partition of the window has exactly 3 replicas -------------------------------
             // Per iteration: 3 x LDS.128, readiness = OR of the three ticket differences, and the KAS:226-234
             // decision from three parallel pairwise compares per slot combined with predicate logic; predicated
@@ -1043,14 +1113,9 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
             }
         }
         }
-        if (valid) {
-            const int i0 = ka_sel4(pb0, o0, o1, o2, 0) >> 4, i1 = ka_sel4(pb1, o0, o1, o2, 0) >> 4, i2 = ka_sel4(pb2, o0, o1, o2, 0) >> 4;
-            int32_t* o = p.out + q * S;
-            o[0] = len > 0 ? __ldg(&p.broker_id[i0]) : -1;
-            if (S > 1) o[1] = len > 1 ? __ldg(&p.broker_id[i1]) : -1;
-            if (S > 2) o[2] = len > 2 ? __ldg(&p.broker_id[i2]) : -1;
-            if (p.out_len) p.out_len[q] = len;
-        }
+        // one byte per partition: the chosen list position of slot 0 and slot 1 (slot 2 is the remaining one);
+        // ka_emit_kernel turns it into broker ids, fully parallel, off the serial chain
+        if (valid) p.pcode[q] = (uint8_t)(pb0 | (pb1 << 2));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) p.ctr8[(i >> 2) * KA_MAX_SLOTS + (i & 3)] = ctr[i];
@@ -1164,4 +1229,25 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order_kernel(const KaOrderPar
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.N * RS; i += blockDim.x) p.ctr8[(i / RS) * KA_MAX_SLOTS + (i % RS)] = ctr[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Emit: (ascending index set, permutation code) -> ordered broker ids + list length. One thread per partition,
+// fully parallel; keeps the id lookups and the 4 B/replica output stream off kernel B's serial chain.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ka_emit_kernel(const int32_t* __restrict__ set, const uint32_t* __restrict__ meta,
+                                                      const uint8_t* __restrict__ pcode, const int32_t* __restrict__ broker_id, int64_t Q,
+                                                      int S, int32_t* __restrict__ out, int32_t* __restrict__ out_len) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int len = (int)(meta[q] & 15u);
+    const int pc = pcode[q];
+    const int b0 = pc & 3, b1 = (pc >> 2) & 3, b2 = 3 - b0 - b1;
+    const int32_t* row = set + q * S;
+    int32_t* o = out + q * S;
+    const int i0 = len > 0 ? row[b0] : -1;
+    o[0] = i0 >= 0 ? __ldg(broker_id + i0) : -1;
+    if (S > 1) { const int i1 = len > 1 ? row[b1] : -1; o[1] = i1 >= 0 ? __ldg(broker_id + i1) : -1; }
+    if (S > 2) { const int i2 = len > 2 ? row[b2] : -1; o[2] = i2 >= 0 ? __ldg(broker_id + i2) : -1; }
+    if (out_len) out_len[q] = len;
 }

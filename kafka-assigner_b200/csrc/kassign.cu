@@ -356,10 +356,6 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         if (const char* e = std::getenv("KA_ORDER_NEAR")) o.near_dist = std::atoi(e);
         o.idle_polls = 4;
         if (const char* e = std::getenv("KA_ORDER_IDLE")) o.idle_polls = (unsigned)std::atoi(e);
-        o.wide = 0;  // measured slower on every BASELINE config; kept as an experiment knob (KA_ORDER_WIDE=1)
-        o.skip_shift = 0;
-        if (const char* e = std::getenv("KA_ORDER_WIDE")) o.wide = std::atoi(e);
-        if (const char* e = std::getenv("KA_ORDER_SKIP_SHIFT")) o.skip_shift = std::atoi(e);
         o.tick4 = c->d_tick4.as<int4>();
         o.idx01 = c->d_idx01.as<uint32_t>();
         o.pcode = c->d_pcode.as<uint8_t>();

@@ -692,8 +692,6 @@ struct KaOrderParams {
     const int4* tick4;        // order3: packed records from ka_ticket_rank_kernel
     const uint32_t* idx01;
     uint8_t* pcode;           // order3: chosen positions (b0 | b1 << 2) per partition, consumed by ka_emit_kernel
-    int wide;                 // RF=3 tight loop: 1 = skip polling while >= 2 commits away (many-warp CTAs)
-    int skip_shift;           // wide: iterations skipped = (distance - 1) >> skip_shift
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -897,60 +895,6 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order4_kernel(const KaOrderPa
 // side by side (independent instruction chains overlap inside the single warp), and commits with
 // predicated stores. No divergent "ready path": an iteration costs the same whether 0 or 32 lanes commit.
 // ------------------------------------------------------------------------------------------------
-// Tight RF=3 loop, "wide" flavour for CTAs with many polling warps (N in the thousands): the loop is then bound by
-// shared-memory bank conflicts of the random 16-byte row reads, not by latency. A lane whose slowest broker is still
-// d >= 2 commits away cannot become ready before d-1 more levels, so it stops polling for (d-1) >> skip_shift
-// iterations (predicated-off loads touch no bank), and a warp in which nobody polls skips the body altogether.
-__device__ __forceinline__ int ka_order3_window_wide(uint32_t a0, uint32_t a1, uint32_t a2, int t0, int t1, int t2, int t10, int t20,
-                                                     int t21, int s2, bool& pending, int skip_shift) {
-    int pcode = 0 | (1 << 2);
-    int skip = 0;
-    uint32_t spins = 0;
-    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0;
-    do {
-        const bool poll = pending && skip == 0;
-        if (__any_sync(KA_FULL, poll)) {
-            const int pp = poll ? 1 : 0;
-            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
-                         : "+r"(r0.x), "+r"(r0.y), "+r"(r0.z), "+r"(r0.w) : "r"(a0), "r"(pp));
-            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
-                         : "+r"(r1.x), "+r"(r1.y), "+r"(r1.z), "+r"(r1.w) : "r"(a1), "r"(pp));
-            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
-                         : "+r"(r2.x), "+r"(r2.y), "+r"(r2.z), "+r"(r2.w) : "r"(a2), "r"(pp));
-            const int e0 = t0 - r0.x - r0.y - (r0.z + r0.w), e1 = t1 - r1.x - r1.y - (r1.z + r1.w), e2 = t2 - r2.x - r2.y - (r2.z + r2.w);
-            const bool commit = poll && (e0 | e1 | e2) == 0;
-            const bool L10 = r1.x < r0.x + t10, L20 = r2.x < r0.x + t20, L21 = r2.x < r1.x + t21;
-            const bool is2 = L10 ? L21 : L20;
-            const bool is1 = L10 && !L21;
-            const int b0 = is2 ? 2 : (is1 ? 1 : 0);
-            const int v0 = is2 ? r2.x : (is1 ? r1.x : r0.x);
-            const uint32_t ad0 = is2 ? a2 : (is1 ? a1 : a0);
-            if (commit) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ad0), "r"(v0 + 1) : "memory");
-            const bool P01 = r1.y < r0.y + s2, P02 = r2.y < r0.y + s2, P12 = r2.y < r1.y + s2;
-            const bool pickhi = is2 ? P01 : (is1 ? P02 : P12);
-            const int lo = (b0 == 0) ? 1 : 0, hi = is2 ? 1 : 2;
-            const int b1 = pickhi ? hi : lo;
-            const int ylo = (b0 == 0) ? r1.y : r0.y, yhi = is2 ? r1.y : r2.y;
-            const int v1 = pickhi ? yhi : ylo;
-            const uint32_t alo = (b0 == 0) ? a1 : a0, ahi = is2 ? a1 : a2;
-            const uint32_t ad1 = pickhi ? ahi : alo;
-            if (commit) asm volatile("st.volatile.shared.s32 [%0+4], %1;" ::"r"(ad1), "r"(v1 + 1) : "memory");
-            const int zlo = (b0 == 0) ? r1.z : r0.z, zhi = is2 ? r1.z : r2.z;
-            const uint32_t ad2 = pickhi ? alo : ahi;
-            const int v2 = pickhi ? zlo : zhi;
-            if (commit) {
-                asm volatile("st.volatile.shared.s32 [%0+8], %1;" ::"r"(ad2), "r"(v2 + 1) : "memory");
-                pcode = b0 | (b1 << 2);
-                pending = false;
-            } else if (poll) {
-                skip = (max(e0, max(e1, e2)) - 1) >> skip_shift;  // distance 1 -> keep polling every iteration
-            }
-        }
-        if (!poll) skip -= (skip > 0);
-    } while (__any_sync(KA_FULL, pending) && ++spins < (1u << 22));
-    return pcode;
-}
-
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderParams p) {
     extern __shared__ __align__(16) unsigned char ka_smem[];
@@ -999,11 +943,7 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
         int pb0 = 0, pb1 = 1, pb2 = 2;
         uint32_t spins = 0;
         const bool all3 = !__any_sync(KA_FULL, pending && len != 3);
-        if (all3 && p.wide) {
-            const int pcode = ka_order3_window_wide(a0, a1, a2, t0, t1, t2, t10, t20, t21, s2, pending, p.skip_shift);
-            if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
-            pb0 = pcode & 3; pb1 = pcode >> 2; pb2 = 3 - pb0 - pb1;
-        } else if (all3) {
+        if (all3) {
             // ---- tight loop: every partition of the window has exactly 3 replicas -------------------------------
             // Per iteration: 3 x LDS.128, readiness = OR of the three ticket differences, and the KAS:226-234
             // decision from three parallel pairwise compares per slot combined with predicate logic; predicated

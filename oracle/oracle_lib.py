@@ -13,19 +13,80 @@ _SRC = os.path.join(_HERE, "kafka_oracle.cpp")
 _LIB = os.path.join(_HERE, "liboracle.so")
 
 
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
 class OracleStatus(ctypes.Structure):
     _fields_ = [("code", ctypes.c_int32), ("topic_index", ctypes.c_int32), ("partition", ctypes.c_int32),
                 ("a", ctypes.c_int32), ("b", ctypes.c_int32), ("message", ctypes.c_char * 256)]
 
 
 def build(force=False):
-    """g++ the restatement into oracle/liboracle.so (gcc only; no reference sources are copied)."""
+    """g++ the restatements into oracle/liboracle.so + libfastoracle.so (gcc only; no reference sources are copied)."""
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _LIB, _SRC])
+    fast_lib()
     return _LIB
 
 
+_FSRC = os.path.join(_HERE, "fast_oracle.cpp")
+_FLIB = os.path.join(_HERE, "libfastoracle.so")
+
+
+class FastStatus(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int32), ("topic_index", ctypes.c_int32), ("partition", ctypes.c_int32),
+                ("a", ctypes.c_int32), ("b", ctypes.c_int32)]
+
+
 _lib = None
+_flib = None
+
+
+def fast_lib():
+    """The optimised flat-array CPU solver (fast_oracle.cpp) — BASELINE.md 'B1' and a third restatement."""
+    global _flib
+    if _flib is None:
+        if not os.path.exists(_FLIB) or os.path.getmtime(_FLIB) < os.path.getmtime(_FSRC):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _FLIB, _FSRC])
+        L = ctypes.CDLL(_FLIB)
+        L.fast_ctx_create.restype = ctypes.c_void_p
+        L.fast_ctx_destroy.argtypes = [ctypes.c_void_p]
+        L.fast_ctx_reset.argtypes = [ctypes.c_void_p]
+        L.fast_solve_dense.restype = ctypes.c_int
+        _flib = L
+    return _flib
+
+
+class FastContext:
+    def __init__(self):
+        self._h = ctypes.c_void_p(fast_lib().fast_ctx_create())
+
+    def reset(self):
+        fast_lib().fast_ctx_reset(self._h)
+
+    def __del__(self):
+        try:
+            fast_lib().fast_ctx_destroy(self._h)
+        except Exception:
+            pass
+
+
+def fast_run_dense(ctx, topic_hash, cur, broker_id, rack_index, desired_rf=-1, out_stride=None):
+    """cur int32 [T,P,RF] -> (out [T*P, S], out_len [T*P], FastStatus). Single thread."""
+    cur = np.ascontiguousarray(cur, dtype=np.int32)
+    T, P, RF = cur.shape
+    S = out_stride or max(RF, desired_rf, 1)
+    th = np.ascontiguousarray(topic_hash, dtype=np.int32)
+    b = np.ascontiguousarray(broker_id, dtype=np.int32)
+    r = np.ascontiguousarray(rack_index, dtype=np.int32)
+    out = np.full((T * P, S), -1, dtype=np.int32)
+    out_len = np.zeros(T * P, dtype=np.int32)
+    st = FastStatus()
+    fast_lib().fast_solve_dense(ctx._h, ctypes.c_int32(T), _p(th), ctypes.c_int32(P), ctypes.c_int32(RF), _p(cur),
+                                ctypes.c_int32(len(b)), _p(b), _p(r), ctypes.c_int32(desired_rf), ctypes.c_int32(S),
+                                _p(out_len), _p(out), ctypes.byref(st))
+    return out, out_len, st
 
 
 def lib():
@@ -48,8 +109,6 @@ def lib():
     return _lib
 
 
-def _p(a):
-    return a.ctypes.data_as(ctypes.c_void_p)
 
 
 class OracleError(Exception):

@@ -138,3 +138,29 @@ def test_synth_generator_is_deterministic_and_feasible(oracle):
     per_topic = out2.reshape(c2.T, -1)
     for t in range(0, c2.T, 97):
         assert np.bincount(per_topic[t] - 1000, minlength=c2.N).max() <= cap  # KAS:65-71 capacity bound
+
+
+def test_fast_cpu_solver_agrees_with_structure_faithful_oracle(oracle):
+    """Third restatement (oracle/fast_oracle.cpp, flat arrays) == kafka_oracle.cpp, successes and failures."""
+    import kafka_assigner_b200 as kab
+    shapes = [dict(T=10, P=8, RF=3, N=6, R=3, n_old=6), dict(T=40, P=33, RF=3, N=64, R=8), dict(T=16, P=100, RF=3, N=30, R=6),
+              dict(T=64, P=17, RF=1, N=11, R=11), dict(T=12, P=96, RF=5, N=35, R=7), dict(T=30, P=48, RF=3, N=60, R=6, remove_frac=0.2, n_old=60),
+              dict(T=30, P=44, RF=3, N=60, R=6, remove_frac=0.2, n_old=60, rack_aware=False)]
+    n_ok = n_err = 0
+    for sh in shapes:
+        for kind in ("structured", "random", "mixed"):
+            cl = kab.synth.make_cluster(seed=0xF00 + sh["T"], kind=kind, **sh)
+            exp, exp_len, est = util.oracle_dense(oracle, cl)
+            got, got_len, st = oracle.fast_run_dense(oracle.FastContext(), cl.topic_hash, cl.cur, cl.broker_id, cl.rack_index)
+            assert (st.code, st.topic_index) == (est.code, est.topic_index), (sh, kind)
+            if est.code == 0:
+                assert np.array_equal(got, exp) and np.array_equal(got_len, exp_len), (sh, kind)
+                n_ok += 1
+            else:
+                assert st.partition == est.partition
+                n_err += 1
+    assert n_ok >= 12
+    c2 = kab.synth.make_config("c2", "mixed")
+    exp, _, _ = util.oracle_dense(oracle, c2)
+    got, _, st = oracle.fast_run_dense(oracle.FastContext(), c2.topic_hash, c2.cur, c2.broker_id, c2.rack_index)
+    assert st.code == 0 and np.array_equal(got, exp)

@@ -21,7 +21,8 @@ def _nvcc():
 
 HOST_DIR = os.path.join(_HERE, "host")
 CLI = os.path.join(_HERE, "bin", "kafka-assignment-generator")
-HOST_SOURCES = ["kafka_assignment_generator.cpp", "kassign_host.hpp"]
+HOST_TEST = os.path.join(_HERE, "bin", "test_kafka_topic_assigner")
+HOST_SOURCES = ["kafka_assignment_generator.cpp", "kassign_host.hpp", "test_kafka_topic_assigner.cpp"]
 
 
 def build_host(force=False):
@@ -33,6 +34,8 @@ def build_host(force=False):
     cmd = ["g++", "-O2", "-std=c++17", "-Wall", os.path.join(HOST_DIR, "kafka_assignment_generator.cpp"), "-L" + CSRC, "-lkassign",
            "-Wl,-rpath,$ORIGIN/../csrc", "-o", CLI]
     subprocess.check_call(cmd)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", os.path.join(HOST_DIR, "test_kafka_topic_assigner.cpp"), "-L" + CSRC,
+                           "-lkassign", "-Wl,-rpath,$ORIGIN/../csrc", "-o", HOST_TEST])
     return CLI
 
 

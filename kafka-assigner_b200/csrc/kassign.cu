@@ -80,15 +80,18 @@ struct ka_ctx {
     cudaEvent_t ev[10] = {};
     float last_ms[8] = {};
     bool ev_valid = false;
+    cudaEvent_t ev_mark = nullptr;  // where enq_sticky_hist records 'kernel A done' (timing only)
     int64_t launches = 0;
     int order_threads = 0;  // leader-order CTA size override (0 = heuristic from N); env KA_ORDER_THREADS wins
+    // second stream + events for the pipelined (super-chunk) solve
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_stage[8] = {};
+    cudaEvent_t ev_pipe[8][5] = {};
+    int last_stages = 1;
+    DevBuf d_seed;
     // staged problem (between the context-free stage and the leader-order stage)
     bool staged = false;
-    int64_t st_Q = 0;
-    int st_S = 0, st_T = 0;
-    int64_t st_L = 0;
-    int st_chunks = 0, st_RS = 4, st_rank_warps = 1, st_rank_grid = 1;
-    size_t st_rank_smem = 0, st_b_smem = 0;
+    struct StagedBlock* staged_block = nullptr;  // StageDesc of ka_stage_dense_device, consumed by ka_order_device
     // async status
     cudaStream_t last_stream = nullptr;
     bool pending_status = false;
@@ -200,44 +203,65 @@ cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-// Stage 1 (context-free, shards across GPUs): kernel A + per-chunk broker histograms. All pointers are
-// device pointers. Leaves the sorted replica sets in ctx scratch for enqueue_order().
-int enqueue_stage(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const int64_t* d_part_off, int P,
-                  const int64_t* d_rep_off, int RF, const int32_t* d_cur, int desired_rf, int S, int Pmax,
-                  int64_t capmax, int64_t Q, ka_status* st) {
+// One contiguous block of topics of a dense or ragged problem, with every device pointer already offset to the block.
+struct StageDesc {
+    int topic_base = 0, T = 0;
+    int64_t Q = 0;                  // partitions in the block
+    const int32_t* d_hash = nullptr;
+    const int64_t* d_part_off = nullptr;  // ragged only (block == whole problem)
+    const int64_t* d_rep_off = nullptr;
+    int P = 0, RF = 0;
+    const int32_t* d_cur = nullptr;
+    int desired_rf = -1, S = 1, Pmax = 0;
+    int64_t capmax = 0;
+    int64_t q0 = 0;                 // first partition row of the block inside the ctx scratch arrays
     Plan pl;
-    c->staged = false;
-    int rc = make_plan(c, Q, S, Pmax, capmax, pl, st);
-    if (rc != KA_OK) return rc;
+};
+
+}  // namespace
+struct StagedBlock { StageDesc d; };
+namespace {
+
+int reserve_scratch(ka_ctx* c, int64_t Qtot, int S, int Ttot, int max_chunks) {
     const int N = c->N;
-
-    KA_CUDA(c->d_set.reserve((size_t)std::max<int64_t>(Q, 1) * S * 4));
-    KA_CUDA(c->d_meta.reserve((size_t)std::max<int64_t>(Q, 1) * 4));
-    KA_CUDA(c->d_ticket.reserve((size_t)std::max<int64_t>(Q, 1) * S * 4));
-    KA_CUDA(c->d_hist.reserve((size_t)pl.num_chunks * std::max(N, 1) * 4));
-    KA_CUDA(c->d_tstatus.reserve((size_t)std::max(T, 1) * sizeof(int4)));
+    KA_CUDA(c->d_set.reserve((size_t)std::max<int64_t>(Qtot, 1) * S * 4));
+    KA_CUDA(c->d_meta.reserve((size_t)std::max<int64_t>(Qtot, 1) * 4));
+    KA_CUDA(c->d_ticket.reserve((size_t)std::max<int64_t>(Qtot, 1) * S * 4));
+    KA_CUDA(c->d_tick4.reserve((size_t)std::max<int64_t>(Qtot, 1) * 16));
+    KA_CUDA(c->d_idx01.reserve((size_t)std::max<int64_t>(Qtot, 1) * 4));
+    KA_CUDA(c->d_pcode.reserve((size_t)std::max<int64_t>(Qtot, 1)));
+    KA_CUDA(c->d_hist.reserve((size_t)std::max(max_chunks, 1) * std::max(N, 1) * 4));
+    KA_CUDA(c->d_seed.reserve((size_t)std::max(N, 1) * 4));
+    KA_CUDA(c->d_tstatus.reserve((size_t)std::max(Ttot, 1) * sizeof(int4)));
     KA_CUDA(c->d_flags.reserve(64));
+    return KA_OK;
+}
 
-    // flags: [0] err_topic = INT_MAX, [1] spin flag = 0
-    c->h_pin->err_topic = INT_MAX;
-    c->h_pin->spin_flag = 0;
-    static const int init_flags[2] = {INT_MAX, 0};
-    KA_CUDA(cudaMemcpyAsync(c->d_flags.p, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, s));
+// flags: [0] lowest failing topic (unsigned atomicMin, 0xFFFFFFFF = none), [1] spin guard (0xFFFFFFFF = not tripped)
+int reset_flags(ka_ctx* c, cudaStream_t s) {
+    c->h_pin->err_topic = -1;
+    c->h_pin->spin_flag = -1;
+    KA_CUDA(cudaMemsetAsync(c->d_flags.p, 0xFF, 2 * sizeof(int), s));
+    return KA_OK;
+}
 
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[1], s));
-
-    if (T > 0) {
+// Context-free part of a block (shards across GPUs): kernel A + per-chunk broker histograms.
+int enq_sticky_hist(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
+    const int N = c->N, S = d.S;
+    const Plan& pl = d.pl;
+    if (d.T > 0) {
         KaSolveParams p{};
-        p.T = T;
-        p.topic_hash = d_hash;
-        p.part_off = d_part_off;
-        p.P = P;
-        p.rep_off = d_rep_off;
-        p.RF = RF;
-        p.cur = d_cur;
-        p.desired_rf = desired_rf;
+        p.T = d.T;
+        p.topic_base = d.topic_base;
+        p.topic_hash = d.d_hash;
+        p.part_off = d.d_part_off;
+        p.P = d.P;
+        p.rep_off = d.d_rep_off;
+        p.RF = d.RF;
+        p.cur = d.d_cur;
+        p.desired_rf = d.desired_rf;
         p.S = S;
-        p.Pmax = Pmax;
+        p.Pmax = d.Pmax;
         p.N = N;
         p.blob = c->d_blob.as<uint16_t>();
         p.blob_bytes = c->blob_bytes;
@@ -252,12 +276,12 @@ int enqueue_stage(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const
         p.range = c->range;
         p.glut = c->d_glut.as<uint16_t>();
         p.broker_id = c->d_broker_id.as<int32_t>();
-        p.set = c->d_set.as<int32_t>();
-        p.meta = c->d_meta.as<uint32_t>();
+        p.set = c->d_set.as<int32_t>() + d.q0 * S;
+        p.meta = c->d_meta.as<uint32_t>() + d.q0;
         p.tstatus = c->d_tstatus.as<int4>();
-        p.err_topic = c->d_flags.as<int>();
+        p.err_topic = c->d_flags.as<unsigned>();
         const int threads = pl.a_warps * 32;
-        int grid = (T + pl.a_warps - 1) / pl.a_warps;
+        int grid = (d.T + pl.a_warps - 1) / pl.a_warps;
         int occ = 1;
         cudaError_t e;
         if (pl.a_load_kind == 0) {
@@ -281,64 +305,64 @@ int enqueue_stage(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const
         KA_CUDA(cudaGetLastError());
         c->launches++;
     }
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[2], s));
-
-    if (Q > 0 && N > 0) {
+    if (c->timing && c->ev_mark) KA_CUDA(cudaEventRecord(c->ev_mark, s));  // end of kernel A
+    if (d.Q > 0 && N > 0) {
         KA_CUDA(allow_smem(ka_ticket_hist_kernel, pl.t_smem_hist));
-        ka_ticket_hist_kernel<<<pl.t_grid_hist, pl.t_warps_hist * 32, pl.t_smem_hist, s>>>(c->d_set.as<int32_t>(), Q, S, N, pl.L, pl.num_chunks,
-                                                                                            c->d_hist.as<int32_t>());
+        ka_ticket_hist_kernel<<<pl.t_grid_hist, pl.t_warps_hist * 32, pl.t_smem_hist, s>>>(c->d_set.as<int32_t>() + d.q0 * S, d.Q, S, N, pl.L,
+                                                                                            pl.num_chunks, c->d_hist.as<int32_t>());
         KA_CUDA(cudaGetLastError());
         c->launches++;
     }
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[6], s));
-    c->staged = true;
-    c->st_Q = Q;
-    c->st_S = S;
-    c->st_T = T;
-    c->st_L = pl.L;
-    c->st_chunks = pl.num_chunks;
-    c->st_RS = pl.RS;
-    c->st_rank_warps = pl.t_warps_rank;
-    c->st_rank_grid = pl.t_grid_rank;
-    c->st_rank_smem = pl.t_smem_rank;
-    c->st_b_smem = pl.b_smem;
     return KA_OK;
 }
 
-// Stage 2 (the serial chain through Context.counter, KAS:202-239): ticket scan + rank, then kernel B.
-int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len, ka_status* st) {
-    if (!c->staged) return set_status(st, KA_ERR_BAD_ARG);
-    const int N = c->N, S = c->st_S;
-    const int64_t Q = c->st_Q;
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[7], s));
+inline bool use_packed(const StageDesc& d) {
     int spec = 1;
     if (const char* e = std::getenv("KA_ORDER_SPEC")) spec = std::atoi(e);
-    const bool packed = c->st_RS == 4 && S <= 3 && spec;  // rows of <= 3 replicas: packed records + emit kernel
-    if (Q > 0 && N > 0) {
-        KA_CUDA(allow_smem(ka_ticket_rank_kernel, c->st_rank_smem));
-        if (packed) {
-            KA_CUDA(c->d_tick4.reserve((size_t)Q * 16));
-            KA_CUDA(c->d_idx01.reserve((size_t)Q * 4));
-            KA_CUDA(c->d_pcode.reserve((size_t)Q));
-        }
-        ka_ticket_scan_kernel<<<(N + 255) / 256, 256, 0, s>>>(c->d_hist.as<int32_t>(), c->st_chunks, N, c->d_ctr8.as<int32_t>(), c->st_RS);
+    return d.pl.RS == 4 && d.S <= 3 && spec;  // rows of <= 3 replicas: packed records + emit kernel
+}
+
+// seed[b] = current counter-row sum: the ticket base of the first block of a solve
+int enq_seed_init(ka_ctx* c, cudaStream_t s, int RS) {
+    if (c->N > 0) {
+        ka_seed_init_kernel<<<(c->N + 255) / 256, 256, 0, s>>>(c->d_ctr8.as<int32_t>(), RS, c->N, c->d_seed.as<int32_t>());
         KA_CUDA(cudaGetLastError());
-        ka_ticket_rank_kernel<<<c->st_rank_grid, c->st_rank_warps * 32, c->st_rank_smem, s>>>(
-            c->d_set.as<int32_t>(), Q, S, N, c->st_L, c->st_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>(),
-            c->d_meta.as<uint32_t>(), packed ? c->d_tick4.as<int4>() : nullptr, packed ? c->d_idx01.as<uint32_t>() : nullptr);
+        c->launches++;
+    }
+    return KA_OK;
+}
+
+// Tickets of a block: exclusive scan of the chunk histograms (seed in -> seed + block totals out) and in-order ranks.
+int enq_tickets(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
+    const int N = c->N, S = d.S;
+    const Plan& pl = d.pl;
+    if (d.Q > 0 && N > 0) {
+        const bool packed = use_packed(d);
+        KA_CUDA(allow_smem(ka_ticket_rank_kernel, pl.t_smem_rank));
+        ka_ticket_scan_kernel<<<(N + 255) / 256, 256, 0, s>>>(c->d_hist.as<int32_t>(), pl.num_chunks, N, c->d_seed.as<int32_t>());
+        KA_CUDA(cudaGetLastError());
+        ka_ticket_rank_kernel<<<pl.t_grid_rank, pl.t_warps_rank * 32, pl.t_smem_rank, s>>>(
+            c->d_set.as<int32_t>() + d.q0 * S, d.Q, S, N, pl.L, pl.num_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>() + d.q0 * S,
+            c->d_meta.as<uint32_t>() + d.q0, packed ? c->d_tick4.as<int4>() + d.q0 : nullptr, packed ? c->d_idx01.as<uint32_t>() + d.q0 : nullptr);
         KA_CUDA(cudaGetLastError());
         c->launches += 2;
     }
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
+    return KA_OK;
+}
 
+// The serial chain through Context.counter (KAS:202-239) for a block + the parallel emit. d_out/d_out_len: block's rows.
+int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out, int32_t* d_out_len) {
+    const int N = c->N, S = d.S;
+    const int64_t Q = d.Q;
     if (Q > 0 && N > 0) {
+        const bool packed = use_packed(d);
         KaOrderParams o{};
         o.Q = Q;
         o.S = S;
         o.N = N;
-        o.set = c->d_set.as<int32_t>();
-        o.ticket = c->d_ticket.as<int32_t>();
-        o.meta = c->d_meta.as<uint32_t>();
+        o.set = c->d_set.as<int32_t>() + d.q0 * S;
+        o.ticket = c->d_ticket.as<int32_t>() + d.q0 * S;
+        o.meta = c->d_meta.as<uint32_t>() + d.q0;
         o.broker_id = c->d_broker_id.as<int32_t>();
         o.ctr8 = c->d_ctr8.as<int32_t>();
         o.out = d_out;
@@ -356,14 +380,15 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
         if (const char* e = std::getenv("KA_ORDER_NEAR")) o.near_dist = std::atoi(e);
         o.idle_polls = 4;
         if (const char* e = std::getenv("KA_ORDER_IDLE")) o.idle_polls = (unsigned)std::atoi(e);
-        o.tick4 = c->d_tick4.as<int4>();
-        o.idx01 = c->d_idx01.as<uint32_t>();
-        o.pcode = c->d_pcode.as<uint8_t>();
+        o.tick4 = c->d_tick4.as<int4>() + d.q0;
+        o.idx01 = c->d_idx01.as<uint32_t>() + d.q0;
+        o.pcode = c->d_pcode.as<uint8_t>() + d.q0;
+        const size_t b_smem = d.pl.b_smem;
         if (packed) {
 #define KA_LAUNCH_ORDER3(NT)                                                        \
     do {                                                                            \
-        KA_CUDA(allow_smem(ka_leader_order3_kernel<NT>, c->st_b_smem));             \
-        ka_leader_order3_kernel<NT><<<1, NT, c->st_b_smem, s>>>(o);                 \
+        KA_CUDA(allow_smem(ka_leader_order3_kernel<NT>, b_smem));                   \
+        ka_leader_order3_kernel<NT><<<1, NT, b_smem, s>>>(o);                       \
     } while (0)
             if (nt >= 1024) KA_LAUNCH_ORDER3(1024);
             else if (nt >= 512) KA_LAUNCH_ORDER3(512);
@@ -371,11 +396,11 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
             else if (nt >= 128) KA_LAUNCH_ORDER3(128);
             else KA_LAUNCH_ORDER3(64);
 #undef KA_LAUNCH_ORDER3
-        } else if (c->st_RS == 4) {
+        } else if (d.pl.RS == 4) {
 #define KA_LAUNCH_ORDER4(NT)                                                        \
     do {                                                                            \
-        KA_CUDA(allow_smem(ka_leader_order4_kernel<NT>, c->st_b_smem));             \
-        ka_leader_order4_kernel<NT><<<1, NT, c->st_b_smem, s>>>(o);                 \
+        KA_CUDA(allow_smem(ka_leader_order4_kernel<NT>, b_smem));                   \
+        ka_leader_order4_kernel<NT><<<1, NT, b_smem, s>>>(o);                       \
     } while (0)
             if (nt >= 1024) KA_LAUNCH_ORDER4(1024);
             else if (nt >= 512) KA_LAUNCH_ORDER4(512);
@@ -383,32 +408,119 @@ int enqueue_order(ka_ctx* c, cudaStream_t s, int32_t* d_out, int32_t* d_out_len,
             else KA_LAUNCH_ORDER4(128);
 #undef KA_LAUNCH_ORDER4
         } else {
-            KA_CUDA(allow_smem(ka_leader_order_kernel<8, 256>, c->st_b_smem));
-            ka_leader_order_kernel<8, 256><<<1, 256, c->st_b_smem, s>>>(o);
+            KA_CUDA(allow_smem(ka_leader_order_kernel<8, 256>, b_smem));
+            ka_leader_order_kernel<8, 256><<<1, 256, b_smem, s>>>(o);
         }
         KA_CUDA(cudaGetLastError());
         c->launches++;
         if (packed) {
-            ka_emit_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(c->d_set.as<int32_t>(), c->d_meta.as<uint32_t>(), c->d_pcode.as<uint8_t>(),
-                                                                     c->d_broker_id.as<int32_t>(), Q, S, d_out, d_out_len);
+            ka_emit_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(o.set, o.meta, o.pcode, c->d_broker_id.as<int32_t>(), Q, S, d_out, d_out_len);
             KA_CUDA(cudaGetLastError());
             c->launches++;
         }
     }
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
-    c->staged = false;
+    return KA_OK;
+}
 
-    // status words back to pinned host memory (async)
+// status words back to pinned host memory (async)
+int enq_flags_readback(ka_ctx* c, cudaStream_t s) {
     KA_CUDA(cudaMemcpyAsync(&c->h_pin->err_topic, c->d_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     return KA_OK;
 }
 
-int enqueue_pipeline(ka_ctx* c, cudaStream_t s, int T, const int32_t* d_hash, const int64_t* d_part_off, int P,
-                     const int64_t* d_rep_off, int RF, const int32_t* d_cur, int desired_rf, int S, int Pmax,
-                     int64_t capmax, int64_t Q, int32_t* d_out, int32_t* d_out_len, ka_status* st) {
-    int rc = enqueue_stage(c, s, T, d_hash, d_part_off, P, d_rep_off, RF, d_cur, desired_rf, S, Pmax, capmax, Q, st);
-    if (rc != KA_OK) return rc;
-    return enqueue_order(c, s, d_out, d_out_len, st);
+// How many topic super-chunks a dense solve is pipelined in (1 = no pipelining).
+int pipeline_stages(int T, int64_t Q) {
+    int k = (Q >= 262144 && T >= 16) ? 4 : 1;
+    if (const char* e = std::getenv("KA_PIPELINE_STAGES")) k = std::atoi(e);
+    return std::max(1, std::min(k, std::min(8, std::max(T, 1))));
+}
+
+// Whole dense solve on `s_main`, pipelined in K topic super-chunks: the aux stream runs (H2D,) kernel A and the ticket
+// kernels of chunk k+1 while s_main runs the leader-order chain of chunk k (and the D2H of its output). Tickets stay
+// exact: chunk k's seed is the previous seed plus the previous chunk's broker totals (ka_ticket_scan_kernel), and
+// s_main orders the chunks strictly one after the other through the counters in ctr8.
+// h_* non-null = host-buffer form (copies inside); d_* always valid device buffers of the full problem.
+int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_rf, int S, const int32_t* h_hash, const int32_t* h_cur,
+              int32_t* d_hash, int32_t* d_cur, int32_t* d_out, int32_t* d_out_len, int32_t* h_out, int32_t* h_out_len, ka_status* st) {
+    const int64_t Q = (int64_t)T * P;
+    const int rf_t = desired_rf >= 0 ? desired_rf : RF;
+    const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
+    const int K = pipeline_stages(T, Q);
+    StageDesc ds[8];
+    int max_chunks = 1;
+    for (int k = 0; k < K; ++k) {
+        const int t0 = (int)((int64_t)T * k / K), t1 = (int)((int64_t)T * (k + 1) / K);
+        StageDesc& d = ds[k];
+        d.topic_base = t0;
+        d.T = t1 - t0;
+        d.q0 = (int64_t)t0 * P;
+        d.Q = (int64_t)d.T * P;
+        d.d_hash = d_hash + t0;
+        d.P = P;
+        d.RF = RF;
+        d.d_cur = d_cur + d.q0 * RF;
+        d.desired_rf = desired_rf;
+        d.S = S;
+        d.Pmax = P;
+        d.capmax = capmax;
+        int rc = make_plan(c, d.Q, S, P, capmax, d.pl, st);
+        if (rc != KA_OK) return rc;
+        max_chunks = std::max(max_chunks, d.pl.num_chunks);
+    }
+    int rc = reserve_scratch(c, Q, S, T, max_chunks);
+    if (rc != KA_OK) return set_status(st, rc);
+    c->last_stages = K;
+    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[0], s_main));
+    if (K == 1) {
+        cudaStream_t s = s_main;
+        StageDesc& d = ds[0];
+        if (h_hash && T > 0) KA_CUDA(cudaMemcpyAsync(d_hash, h_hash, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+        if (h_cur && Q * RF > 0) KA_CUDA(cudaMemcpyAsync(d_cur, h_cur, (size_t)Q * RF * 4, cudaMemcpyHostToDevice, s));
+        if ((rc = reset_flags(c, s)) != KA_OK) return rc;
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev[1], s));
+        c->ev_mark = c->ev[2];
+        if ((rc = enq_sticky_hist(c, s, d)) != KA_OK) return rc;
+        c->ev_mark = nullptr;
+        if ((rc = enq_seed_init(c, s, d.pl.RS)) != KA_OK) return rc;
+        if ((rc = enq_tickets(c, s, d)) != KA_OK) return rc;
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
+        if ((rc = enq_order_emit(c, s, d, d_out, d_out_len)) != KA_OK) return rc;
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
+        if (h_out && Q > 0 && c->N > 0) {
+            KA_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)Q * S * 4, cudaMemcpyDeviceToHost, s));
+            if (h_out_len) KA_CUDA(cudaMemcpyAsync(h_out_len, d_out_len, (size_t)Q * 4, cudaMemcpyDeviceToHost, s));
+        }
+    } else {
+        cudaStream_t aux = c->aux;
+        KA_CUDA(cudaEventRecord(c->ev_in, s_main));           // inputs ready / earlier work on s_main done
+        KA_CUDA(cudaStreamWaitEvent(aux, c->ev_in, 0));
+        if ((rc = reset_flags(c, aux)) != KA_OK) return rc;
+        if ((rc = enq_seed_init(c, aux, ds[0].pl.RS)) != KA_OK) return rc;
+        for (int k = 0; k < K; ++k) {
+            StageDesc& d = ds[k];
+            if (h_hash && d.T > 0) KA_CUDA(cudaMemcpyAsync(d_hash + d.topic_base, h_hash + d.topic_base, (size_t)d.T * 4, cudaMemcpyHostToDevice, aux));
+            if (h_cur && d.Q * RF > 0)
+                KA_CUDA(cudaMemcpyAsync(d_cur + d.q0 * RF, h_cur + d.q0 * RF, (size_t)d.Q * RF * 4, cudaMemcpyHostToDevice, aux));
+            if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][0], aux));
+            c->ev_mark = c->timing ? c->ev_pipe[k][1] : nullptr;
+            if ((rc = enq_sticky_hist(c, aux, d)) != KA_OK) return rc;
+            c->ev_mark = nullptr;
+            if ((rc = enq_tickets(c, aux, d)) != KA_OK) return rc;
+            if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][2], aux));
+            KA_CUDA(cudaEventRecord(c->ev_stage[k], aux));
+            KA_CUDA(cudaStreamWaitEvent(s_main, c->ev_stage[k], 0));
+            if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][3], s_main));
+            if ((rc = enq_order_emit(c, s_main, d, d_out + d.q0 * S, d_out_len ? d_out_len + d.q0 : nullptr)) != KA_OK) return rc;
+            if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][4], s_main));
+            if (h_out && d.Q > 0 && c->N > 0) {
+                KA_CUDA(cudaMemcpyAsync(h_out + d.q0 * S, d_out + d.q0 * S, (size_t)d.Q * S * 4, cudaMemcpyDeviceToHost, s_main));
+                if (h_out_len) KA_CUDA(cudaMemcpyAsync(h_out_len + d.q0, d_out_len + d.q0, (size_t)d.Q * 4, cudaMemcpyDeviceToHost, s_main));
+            }
+        }
+    }
+    if ((rc = enq_flags_readback(c, s_main)) != KA_OK) return rc;
+    if (c->timing) { KA_CUDA(cudaEventRecord(c->ev[5], s_main)); c->ev_valid = true; }
+    return KA_OK;
 }
 
 // Wait for the stream, translate device flags into a ka_status.
@@ -419,7 +531,7 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
     r.code = KA_OK;
     r.topic_index = -1;
     r.partition = -1;
-    if (c->h_pin->err_topic != INT_MAX) {
+    if (c->h_pin->err_topic != -1) {
         const int t = c->h_pin->err_topic;
         KA_CUDA(cudaMemcpy(&c->h_pin->tstatus, c->d_tstatus.as<int4>() + t, sizeof(int4), cudaMemcpyDeviceToHost));
         r.code = c->h_pin->tstatus.x;
@@ -429,21 +541,30 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
         if (ord >= 0 && c->last_part_id && c->last_part_off) r.partition = c->last_part_id[c->last_part_off[t] + ord];
         r.a = c->h_pin->tstatus.z;
         r.b = c->h_pin->tstatus.w;
-    } else if (c->h_pin->spin_flag != 0) {
+    } else if (c->h_pin->spin_flag != -1) {
         r.code = KA_ERR_CUDA;
         std::fprintf(stderr, "[kassign] internal error: leader-order dataflow guard tripped\n");
     }
     if (c->timing && c->ev_valid) {
         for (int i = 0; i < 8; ++i) c->last_ms[i] = 0.f;
-        cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]);  // H2D
-        cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]);  // kernel A
-        float t1 = 0.f, t2 = 0.f;
-        cudaEventElapsedTime(&t1, c->ev[2], c->ev[6]);             // ticket histogram (stage 1)
-        cudaEventElapsedTime(&t2, c->ev[7], c->ev[3]);             // ticket scan + rank (stage 2)
-        c->last_ms[1] = t1 + t2;
-        cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);  // kernel B
-        cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);  // D2H
-        cudaEventElapsedTime(&c->last_ms[5], c->ev[0], c->ev[5]);  // total
+        cudaEventElapsedTime(&c->last_ms[5], c->ev[0], c->ev[5]);  // total on the stream
+        if (c->last_stages <= 1) {
+            cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]);  // H2D
+            cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]);  // kernel A
+            cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);  // tickets (hist + seed + scan + rank)
+            cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);  // kernel B + emit
+            cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);  // D2H
+        } else {  // pipelined: phases of different chunks overlap; report the per-phase sums
+            for (int k = 0; k < c->last_stages; ++k) {
+                float a = 0.f, t = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, c->ev_pipe[k][0], c->ev_pipe[k][1]);
+                cudaEventElapsedTime(&t, c->ev_pipe[k][1], c->ev_pipe[k][2]);
+                cudaEventElapsedTime(&b, c->ev_pipe[k][3], c->ev_pipe[k][4]);
+                c->last_ms[0] += a;
+                c->last_ms[1] += t;
+                c->last_ms[2] += b;
+            }
+        }
     }
     c->last = r;
     if (st) *st = r;
@@ -511,6 +632,11 @@ ka_ctx* ka_ctx_create(int32_t device) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
     if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_pin), sizeof(HostPinned), cudaHostAllocDefault) != cudaSuccess) { delete c; return nullptr; }
     for (auto& e : c->ev) cudaEventCreate(&e);
+    if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    for (auto& e : c->ev_stage) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& row : c->ev_pipe)
+        for (auto& e : row) cudaEventCreate(&e);
     return c;
 }
 
@@ -519,12 +645,18 @@ void ka_ctx_destroy(ka_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_blob, &c->d_glut, &c->d_broker_id, &c->d_ctr8, &c->d_hash, &c->d_part_off, &c->d_rep_off, &c->d_cur, &c->d_set,
-                      &c->d_meta, &c->d_ticket, &c->d_tick4, &c->d_idx01, &c->d_pcode, &c->d_out, &c->d_out_len, &c->d_hist, &c->d_tstatus, &c->d_flags})
+                      &c->d_meta, &c->d_ticket, &c->d_tick4, &c->d_idx01, &c->d_pcode, &c->d_seed, &c->d_out, &c->d_out_len, &c->d_hist, &c->d_tstatus, &c->d_flags})
         b->release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
+    if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    for (auto& e : c->ev_stage) if (e) cudaEventDestroy(e);
+    for (auto& row : c->ev_pipe)
+        for (auto& e : row) if (e) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
+    delete c->staged_block;
     delete c;
 }
 
@@ -694,16 +826,12 @@ int32_t ka_solve_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     if (cudaSetDevice(c->device) != cudaSuccess) return set_status(st, KA_ERR_CUDA);
     if (c->pending_status) finish_status(c, c->last_stream, nullptr);
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t Q = (int64_t)T * P;
-    const int rf_t = desired_rf >= 0 ? desired_rf : RF;
-    const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
     c->last_part_id = nullptr;
     c->last_part_off = nullptr;
-    if (c->timing) { cudaEventRecord(c->ev[0], s); }
-    rc = enqueue_pipeline(c, s, T, d_topic_hash, nullptr, P, nullptr, RF, d_cur_broker, desired_rf, out_stride, P, capmax, Q,
-                          d_out_broker, d_out_len, st);
+    c->staged = false;
+    rc = run_dense(c, s, T, P, RF, desired_rf, out_stride, nullptr, nullptr, const_cast<int32_t*>(d_topic_hash),
+                   const_cast<int32_t*>(d_cur_broker), d_out_broker, d_out_len, nullptr, nullptr, st);
     if (rc != KA_OK) return rc;
-    if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
     c->last_stream = s;
     c->pending_status = true;
     if (st) return finish_status(c, s, st);
@@ -718,22 +846,52 @@ int32_t ka_stage_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     if (cudaSetDevice(c->device) != cudaSuccess) return KA_ERR_CUDA;
     if (c->pending_status) finish_status(c, c->last_stream, nullptr);
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t Q = (int64_t)T * P;
+    if (!c->staged_block) c->staged_block = new StagedBlock();
+    StageDesc& d = c->staged_block->d;
+    d = StageDesc();
+    d.T = T;
+    d.Q = (int64_t)T * P;
+    d.d_hash = d_topic_hash;
+    d.P = P;
+    d.RF = RF;
+    d.d_cur = d_cur_broker;
+    d.desired_rf = desired_rf;
+    d.S = out_stride;
+    d.Pmax = P;
     const int rf_t = desired_rf >= 0 ? desired_rf : RF;
-    const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
+    d.capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
+    c->staged = false;
+    rc = make_plan(c, d.Q, d.S, d.Pmax, d.capmax, d.pl, &lst);
+    if (rc != KA_OK) return rc;
+    if ((rc = reserve_scratch(c, d.Q, d.S, T, d.pl.num_chunks)) != KA_OK) return rc;
     c->last_part_id = nullptr;
     c->last_part_off = nullptr;
-    if (c->timing) { cudaEventRecord(c->ev[0], s); }
-    return enqueue_stage(c, s, T, d_topic_hash, nullptr, P, nullptr, RF, d_cur_broker, desired_rf, out_stride, P, capmax, Q, &lst);
+    c->last_stages = 1;
+    if (c->timing) { cudaEventRecord(c->ev[0], s); cudaEventRecord(c->ev[1], s); }
+    if ((rc = reset_flags(c, s)) != KA_OK) return rc;
+    c->ev_mark = c->timing ? c->ev[2] : nullptr;
+    rc = enq_sticky_hist(c, s, d);
+    c->ev_mark = nullptr;
+    if (rc != KA_OK) return rc;
+    c->staged = true;
+    return KA_OK;
 }
 
 int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st) {
     if (!c) return set_status(st, KA_ERR_NO_DEVICE);
     if (cudaSetDevice(c->device) != cudaSuccess) return set_status(st, KA_ERR_CUDA);
+    if (!c->staged || !c->staged_block) return set_status(st, KA_ERR_BAD_ARG);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = enqueue_order(c, s, d_out_broker, d_out_len, st);
-    if (rc != KA_OK) return rc;
+    const StageDesc& d = c->staged_block->d;
+    int rc;
+    if ((rc = enq_seed_init(c, s, d.pl.RS)) != KA_OK) return set_status(st, rc);
+    if ((rc = enq_tickets(c, s, d)) != KA_OK) return set_status(st, rc);
+    if (c->timing) cudaEventRecord(c->ev[3], s);
+    if ((rc = enq_order_emit(c, s, d, d_out_broker, d_out_len)) != KA_OK) return set_status(st, rc);
+    if (c->timing) cudaEventRecord(c->ev[4], s);
+    if ((rc = enq_flags_readback(c, s)) != KA_OK) return set_status(st, rc);
     if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
+    c->staged = false;
     c->last_stream = s;
     c->pending_status = true;
     if (st) return finish_status(c, s, st);
@@ -754,23 +912,12 @@ int32_t ka_solve_dense(ka_ctx* c, int32_t T, const int32_t* topic_hash, int32_t 
     KA_CUDA(c->d_cur.reserve((size_t)std::max<int64_t>(R, 1) * 4));
     KA_CUDA(c->d_out.reserve((size_t)std::max<int64_t>(Q, 1) * out_stride * 4));
     KA_CUDA(c->d_out_len.reserve((size_t)std::max<int64_t>(Q, 1) * 4));
-    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[0], s));
-    if (T > 0) KA_CUDA(cudaMemcpyAsync(c->d_hash.p, topic_hash, (size_t)T * 4, cudaMemcpyHostToDevice, s));
-    if (R > 0) KA_CUDA(cudaMemcpyAsync(c->d_cur.p, cur_broker, (size_t)R * 4, cudaMemcpyHostToDevice, s));
-    const int rf_t = desired_rf >= 0 ? desired_rf : RF;
-    const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
     c->last_part_id = nullptr;
     c->last_part_off = nullptr;
-    rc = enqueue_pipeline(c, s, T, c->d_hash.as<int32_t>(), nullptr, P, nullptr, RF, c->d_cur.as<int32_t>(), desired_rf, out_stride, P,
-                          capmax, Q, c->d_out.as<int32_t>(), out_len ? c->d_out_len.as<int32_t>() : nullptr, st);
+    c->staged = false;
+    rc = run_dense(c, s, T, P, RF, desired_rf, out_stride, topic_hash, cur_broker, c->d_hash.as<int32_t>(), c->d_cur.as<int32_t>(),
+                   c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>(), out_broker, out_len, st);
     if (rc != KA_OK) return rc;
-    if (Q > 0) {
-        if (c->N > 0) {
-            KA_CUDA(cudaMemcpyAsync(out_broker, c->d_out.p, (size_t)Q * out_stride * 4, cudaMemcpyDeviceToHost, s));
-            if (out_len) KA_CUDA(cudaMemcpyAsync(out_len, c->d_out_len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, s));
-        }
-    }
-    if (c->timing) { KA_CUDA(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
     c->last_stream = s;
     c->pending_status = true;
     ka_status local;
@@ -821,6 +968,22 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     KA_CUDA(c->d_cur.reserve((size_t)std::max<int64_t>(R, 1) * 4));
     KA_CUDA(c->d_out.reserve((size_t)std::max<int64_t>(Q, 1) * S * 4));
     KA_CUDA(c->d_out_len.reserve((size_t)std::max<int64_t>(Q, 1) * 4));
+    StageDesc d;
+    d.T = T;
+    d.Q = Q;
+    d.d_hash = c->d_hash.as<int32_t>();
+    d.d_part_off = c->d_part_off.as<int64_t>();
+    d.d_rep_off = c->d_rep_off.as<int64_t>();
+    d.d_cur = c->d_cur.as<int32_t>();
+    d.desired_rf = desired_rf;
+    d.S = S;
+    d.Pmax = Pmax;
+    d.capmax = capmax;
+    c->staged = false;
+    int rc = make_plan(c, Q, S, Pmax, capmax, d.pl, st);
+    if (rc != KA_OK) return rc;
+    if ((rc = reserve_scratch(c, Q, S, T, d.pl.num_chunks)) != KA_OK) return set_status(st, rc);
+    c->last_stages = 1;
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[0], s));
     if (T > 0) {
         KA_CUDA(cudaMemcpyAsync(c->d_hash.p, topic_hash, (size_t)T * 4, cudaMemcpyHostToDevice, s));
@@ -828,16 +991,24 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     }
     if (Q > 0) KA_CUDA(cudaMemcpyAsync(c->d_rep_off.p, rep_off, (size_t)(Q + 1) * 8, cudaMemcpyHostToDevice, s));
     if (R > 0) KA_CUDA(cudaMemcpyAsync(c->d_cur.p, cur_broker, (size_t)R * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = reset_flags(c, s)) != KA_OK) return set_status(st, rc);
+    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[1], s));
     c->last_part_id = part_id;
     c->last_part_off = part_off;
-    int rc = enqueue_pipeline(c, s, T, c->d_hash.as<int32_t>(), c->d_part_off.as<int64_t>(), 0, c->d_rep_off.as<int64_t>(), 0,
-                              c->d_cur.as<int32_t>(), desired_rf, S, Pmax, capmax, Q, c->d_out.as<int32_t>(),
-                              out_len ? c->d_out_len.as<int32_t>() : nullptr, st);
-    if (rc != KA_OK) return rc;
+    c->ev_mark = c->timing ? c->ev[2] : nullptr;
+    rc = enq_sticky_hist(c, s, d);
+    c->ev_mark = nullptr;
+    if (rc != KA_OK) return set_status(st, rc);
+    if ((rc = enq_seed_init(c, s, d.pl.RS)) != KA_OK) return set_status(st, rc);
+    if ((rc = enq_tickets(c, s, d)) != KA_OK) return set_status(st, rc);
+    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
+    if ((rc = enq_order_emit(c, s, d, c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>())) != KA_OK) return set_status(st, rc);
+    if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
     if (Q > 0 && c->N > 0) {
         KA_CUDA(cudaMemcpyAsync(out_broker, c->d_out.p, (size_t)Q * S * 4, cudaMemcpyDeviceToHost, s));
         if (out_len) KA_CUDA(cudaMemcpyAsync(out_len, c->d_out_len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, s));
     }
+    if ((rc = enq_flags_readback(c, s)) != KA_OK) return set_status(st, rc);
     if (c->timing) { KA_CUDA(cudaEventRecord(c->ev[5], s)); c->ev_valid = true; }
     c->last_stream = s;
     c->pending_status = true;

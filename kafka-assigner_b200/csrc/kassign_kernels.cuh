@@ -35,6 +35,7 @@ enum { KA_LUT_SMEM = 0, KA_LUT_GLOBAL = 1, KA_LUT_BSEARCH = 2 };
 struct KaSolveParams {
     // problem
     int T;
+    int topic_base;             // index of this block's first topic in the whole run (status reporting)
     const int32_t* topic_hash;  // [T]
     const int64_t* part_off;    // [T+1] or nullptr (dense: P partitions per topic)
     int P;
@@ -63,7 +64,7 @@ struct KaSolveParams {
     int32_t* set;               // [Q*S] accepted broker indices, ascending per row, -1 padded
     uint32_t* meta;             // [Q] len | rotation bits
     int4* tstatus;              // [T] per-topic error record (written only on error)
-    int* err_topic;             // atomicMin of failing topic index (init = INT_MAX)
+    unsigned* err_topic;        // unsigned atomicMin of the failing topic index (init = 0xFFFFFFFF)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -511,8 +512,8 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
         for (int e = lane; e < P * S; e += 32) oset[e] = -1;
         for (int pp = lane; pp < P; pp += 32) p.meta[g0 + pp] = 0u;
         if (lane == 0) {
-            p.tstatus[t] = make_int4(err, errp, erra, errb);
-            atomicMin(p.err_topic, t);
+            p.tstatus[p.topic_base + t] = make_int4(err, errp, erra, errb);
+            atomicMin(p.err_topic, (unsigned)(p.topic_base + t));
         }
     }
     __syncwarp();
@@ -585,14 +586,23 @@ __global__ void __launch_bounds__(1024) ka_ticket_hist_kernel(const int32_t* __r
     }
 }
 
-// Exclusive scan over chunks, per broker, seeded with the broker's current counter-row sum. One thread per
-// broker (coalesced across brokers); loads are batched 8 deep so the column walk is not one long
-// load->store->load dependency chain.
-__global__ void ka_ticket_scan_kernel(int32_t* hist, int num_chunks, int N, const int32_t* __restrict__ ctr8, int RS) {
+// seed[b] = sum of broker b's counter row = number of partitions that have committed on b so far (every commit adds
+// exactly one to exactly one slot of each of its brokers): the ticket base of the first block of a solve.
+__global__ void ka_seed_init_kernel(const int32_t* __restrict__ ctr8, int RS, int N, int32_t* __restrict__ seed) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= N) return;
     int run = 0;
     for (int r = 0; r < RS; ++r) run += ctr8[b * KA_MAX_SLOTS + r];
+    seed[b] = run;
+}
+
+// Exclusive scan over chunks, per broker, seeded with seed[b]; leaves seed[b] + (block total of b) in seed[b] so the
+// next block of a pipelined solve continues the numbering without reading live counters. One thread per broker
+// (coalesced across brokers); loads are batched 8 deep so the column walk is not one long load->store->load chain.
+__global__ void ka_ticket_scan_kernel(int32_t* hist, int num_chunks, int N, int32_t* seed) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    int run = seed[b];
     int c = 0;
     for (; c + 8 <= num_chunks; c += 8) {
         int v[8];
@@ -609,6 +619,7 @@ __global__ void ka_ticket_scan_kernel(int32_t* hist, int num_chunks, int N, cons
         hist[(size_t)c * N + b] = run;
         run += v;
     }
+    seed[b] = run;
 }
 
 // When tick4/idx01 are given (rows of <= 3 replicas) the pass also emits the packed per-partition record kernel B

@@ -112,3 +112,11 @@ def test_reassignment_errors_abort_without_new_assignment(cli, snapshot):
     assert "java.lang.IllegalStateException: Topic events has a higher replication factor (3) than available brokers!" in err
     rc, out, err = run(cli, "--zk_string", snapshot, "--mode", "PRINT_REASSIGNMENT", "--topics", "test,missing")
     assert rc != 0 and "NullPointerException" in err and "NEW ASSIGNMENT" not in out   # KTA:51
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_passes_the_reference_junit_suite(cli):
+    """host/test_kafka_topic_assigner.cpp: KafkaTopicAssignerTest.java re-expressed against kassign::KafkaTopicAssigner."""
+    r = subprocess.run([kab.build_mod.HOST_TEST], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("OK")

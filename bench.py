@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4shard", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4shard", "c4", "c5"])
     ap.add_argument("--kind", default="mixed", choices=["mixed", "structured", "random"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")

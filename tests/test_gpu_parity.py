@@ -411,3 +411,19 @@ def test_pipelined_super_chunks_are_exact(native_lib, oracle):
     _, _, est = util.oracle_dense(oracle, bad)
     assert est.code == 4 and est.topic_index >= 10      # fails in the 2nd or 3rd chunk of 3
     assert np.load("/tmp/_pl_bad.npy").tolist() == [est.code, est.topic_index, est.partition]
+
+
+def test_large_capacity_load_counters_and_size_limit(native_lib, oracle):
+    """cap = ceil(P*RF/N) > 255 switches kernel A's per-broker load counters to 16-bit; absurd sizes are refused."""
+    cl = kab.synth.make_cluster(T=3, P=700, RF=2, N=4, R=2, seed=12, kind="random", n_old=4)   # cap = 350
+    exp, exp_len, est = util.oracle_dense(oracle, cl)
+    out, out_len, st = kab.Solver(0).solve_cluster(cl, check=False)
+    assert (st.code, st.topic_index, st.partition) == (est.code, est.topic_index, est.partition)
+    if est.code == 0:
+        assert np.array_equal(out.reshape(-1, 2), exp)
+    # one topic with 200k partitions does not fit a warp's shared-memory slab: a clean KA_ERR_LIMIT, not a crash
+    s = kab.Solver(0)
+    s.set_brokers(np.arange(1, 9, dtype=np.int32), np.arange(8, dtype=np.int32) % 4)
+    cur = np.tile(np.array([[1, 2]], dtype=np.int32), (1, 200000, 1))
+    _, _, st = s.solve_dense(np.array([7], dtype=np.int32), cur, check=False)
+    assert st.code == kab._native.KA_ERR_LIMIT

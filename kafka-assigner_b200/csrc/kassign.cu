@@ -430,7 +430,9 @@ int enq_flags_readback(ka_ctx* c, cudaStream_t s) {
 
 // How many topic super-chunks a dense solve is pipelined in (1 = no pipelining).
 int pipeline_stages(int T, int64_t Q) {
-    int k = (Q >= 262144 && T >= 16) ? 4 : 1;
+    // worthwhile only when every chunk still has enough topics to keep kernel A throughput-bound (a topic is one warp:
+    // with few topics per chunk A is latency-bound and K chunks cost K times as much — measured on config 5)
+    int k = Q >= 262144 ? std::min(4, T / 2048) : 1;
     if (const char* e = std::getenv("KA_PIPELINE_STAGES")) k = std::atoi(e);
     return std::max(1, std::min(k, std::min(8, std::max(T, 1))));
 }

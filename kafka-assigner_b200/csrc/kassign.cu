@@ -182,8 +182,13 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, Plan& pl, k
     pl.t_warps_hist = (int)std::max<size_t>(1, std::min<size_t>(32, KA_SMEM_BUDGET / hist_pw));
     pl.t_warps_rank = (int)std::max<size_t>(1, std::min<size_t>(32, KA_SMEM_BUDGET / rank_pw));
     const int64_t max_conc = (int64_t)c->sm_count * pl.t_warps_rank;
-    int64_t nc = (int64_t)std::ceil(std::sqrt(5.0 * (double)std::max<int64_t>(windows, 1)));
-    nc = std::max<int64_t>(1, std::min<int64_t>(nc, std::min<int64_t>(max_conc, std::max<int64_t>(windows, 1))));
+    // chunks: enough to fill the machine with short in-order rank walks (~8 windows each); the scan is a warp-per-broker
+    // shuffle scan whose cost is its (strided) traffic chunks x N x 4 B — keep that to a few MB (measured: C5 regresses
+    // beyond it) and within KA_SCAN_MAX_CHUNKS.
+    int64_t nc = (std::max<int64_t>(windows, 1) + 7) / 8;
+    nc = std::min<int64_t>(nc, std::min<int64_t>(KA_SCAN_MAX_CHUNKS, std::max<int64_t>(64, 3500000 / std::max(N, 1))));
+    (void)max_conc;
+    nc = std::max<int64_t>(1, std::min<int64_t>(nc, std::max<int64_t>(windows, 1)));
     int64_t wpc = (std::max<int64_t>(windows, 1) + nc - 1) / nc;  // windows per chunk
     pl.L = wpc * 32;
     pl.num_chunks = (int)((std::max<int64_t>(windows, 1) + wpc - 1) / wpc);
@@ -339,7 +344,7 @@ int enq_tickets(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
     if (d.Q > 0 && N > 0) {
         const bool packed = use_packed(d);
         KA_CUDA(allow_smem(ka_ticket_rank_kernel, pl.t_smem_rank));
-        ka_ticket_scan_kernel<<<(N + 255) / 256, 256, 0, s>>>(c->d_hist.as<int32_t>(), pl.num_chunks, N, c->d_seed.as<int32_t>());
+        ka_ticket_scan_kernel<<<(N + 7) / 8, 256, 0, s>>>(c->d_hist.as<int32_t>(), pl.num_chunks, N, c->d_seed.as<int32_t>());
         KA_CUDA(cudaGetLastError());
         ka_ticket_rank_kernel<<<pl.t_grid_rank, pl.t_warps_rank * 32, pl.t_smem_rank, s>>>(
             c->d_set.as<int32_t>() + d.q0 * S, d.Q, S, N, pl.L, pl.num_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>() + d.q0 * S,

@@ -597,29 +597,36 @@ __global__ void ka_seed_init_kernel(const int32_t* __restrict__ ctr8, int RS, in
 }
 
 // Exclusive scan over chunks, per broker, seeded with seed[b]; leaves seed[b] + (block total of b) in seed[b] so the
-// next block of a pipelined solve continues the numbering without reading live counters. One thread per broker
-// (coalesced across brokers); loads are batched 8 deep so the column walk is not one long load->store->load chain.
-__global__ void ka_ticket_scan_kernel(int32_t* hist, int num_chunks, int N, int32_t* seed) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// next block of a pipelined solve continues the numbering without reading live counters. One WARP per broker: lane l
+// owns chunks l, l+32, ...; every load of the column is in flight at once, then a shuffle scan per 32-chunk tile carries
+// the running total (num_chunks <= KA_SCAN_MAX_CHUNKS).
+#define KA_SCAN_MAX_CHUNKS 2048
+__global__ void __launch_bounds__(256) ka_ticket_scan_kernel(int32_t* hist, int num_chunks, int N, int32_t* seed) {
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= N) return;
     int run = seed[b];
-    int c = 0;
-    for (; c + 8 <= num_chunks; c += 8) {
+    for (int c0 = 0; c0 < num_chunks; c0 += 256) {  // 8 tiles of 32 chunks per round: 8 independent loads per lane
         int v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = hist[(size_t)(c + u) * N + b];
+        for (int t = 0; t < 8; ++t) {
+            const int c = c0 + t * 32 + lane;
+            v[t] = c < num_chunks ? hist[(size_t)c * N + b] : 0;
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            hist[(size_t)(c + u) * N + b] = run;
-            run += v[u];
+        for (int t = 0; t < 8; ++t) {
+            int x = v[t];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(KA_FULL, x, o);
+                if (lane >= o) x += y;
+            }
+            const int c = c0 + t * 32 + lane;
+            if (c < num_chunks) hist[(size_t)c * N + b] = run + x - v[t];  // exclusive
+            run += __shfl_sync(KA_FULL, x, 31);
         }
     }
-    for (; c < num_chunks; ++c) {
-        const int v = hist[(size_t)c * N + b];
-        hist[(size_t)c * N + b] = run;
-        run += v;
-    }
-    seed[b] = run;
+    if (lane == 0) seed[b] = run;
 }
 
 // When tick4/idx01 are given (rows of <= 3 replicas) the pass also emits the packed per-partition record kernel B

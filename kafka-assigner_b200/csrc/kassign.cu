@@ -379,12 +379,6 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
         int nt = N < 400 ? 128 : (N < 2500 ? 256 : (N < 7500 ? 512 : 1024));
         if (c->order_threads > 0) nt = c->order_threads;
         if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
-        o.sleep_ns = 0;
-        o.near_dist = 1;
-        if (const char* e = std::getenv("KA_ORDER_SLEEP_NS")) o.sleep_ns = (unsigned)std::atoi(e);
-        if (const char* e = std::getenv("KA_ORDER_NEAR")) o.near_dist = std::atoi(e);
-        o.idle_polls = 4;
-        if (const char* e = std::getenv("KA_ORDER_IDLE")) o.idle_polls = (unsigned)std::atoi(e);
         o.tick4 = c->d_tick4.as<int4>() + d.q0;
         o.idx01 = c->d_idx01.as<uint32_t>() + d.q0;
         o.pcode = c->d_pcode.as<uint8_t>() + d.q0;

@@ -704,9 +704,6 @@ struct KaOrderParams {
     int32_t* out;             // [Q*S] broker ids, leader first
     int32_t* out_len;         // [Q] or nullptr
     int* err_flag;            // set to KA_E_INTERNAL_SPIN if a window spins beyond the guard
-    unsigned sleep_ns;        // back-off of warps with no partition near its turn (0 = spin)
-    int near_dist;            // "near" = at most this many commits away on the slowest broker
-    unsigned idle_polls;      // speculative kernel: polls without any commit in the warp before it backs off
     const int4* tick4;        // order3: packed records from ka_ticket_rank_kernel
     const uint32_t* idx01;
     uint8_t* pcode;           // order3: chosen positions (b0 | b1 << 2) per partition, consumed by ka_emit_kernel
@@ -879,14 +876,8 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order4_kernel(const KaOrderPa
                     pending = false;
                 }
             }
-            const uint32_t pend = __ballot_sync(KA_FULL, pending);
-            if (pend == 0u) break;  // every lane of the window has committed
-            const uint32_t near = __ballot_sync(KA_FULL, pending && d <= p.near_dist);
-            if (near == 0u && p.sleep_ns > 0) {
-                // nobody in this warp can commit before more commits land on its brokers: yield the issue slots
-                // and the shared-memory port to the warps at the frontier.
-                __nanosleep(p.sleep_ns);
-            }
+            if (!__any_sync(KA_FULL, pending)) break;  // every lane of the window has committed
+            // (a __nanosleep back-off for warps far from the frontier was measured: no gain on any config)
             if (++spins > (1u << 22)) {  // guard: a ticket/set inconsistency must not hang the GPU
                 if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
                 break;
@@ -1009,7 +1000,6 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
             if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);  // guard tripped: ticket/set inconsistency
             pb0 = pcode & 3; pb1 = pcode >> 2; pb2 = 3 - pb0 - pb1;
         } else {
-        uint32_t idle = 0;
         for (;;) {
             int4 r0, r1, r2;
             asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
@@ -1056,15 +1046,7 @@ __global__ void __launch_bounds__(NT, 1) ka_leader_order3_kernel(const KaOrderPa
                 pending = false;
                 a0 = a1 = a2 = cbase;
             }
-            const uint32_t cm_mask = __ballot_sync(KA_FULL, commit);
             if (!__any_sync(KA_FULL, pending)) break;  // every lane of the window has committed
-            if (cm_mask) {
-                idle = 0;
-            } else if (++idle > p.idle_polls && p.sleep_ns > 0) {
-                // nothing in this warp moved for a while: it is waiting on warps at the frontier — yield the issue
-                // slots and the shared-memory port to them.
-                __nanosleep(p.sleep_ns);
-            }
             if (++spins > (1u << 22)) {  // guard: a ticket/set inconsistency must not hang the GPU
                 if (pending) atomicExch(p.err_flag, KA_E_INTERNAL_SPIN);
                 break;

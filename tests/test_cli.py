@@ -120,3 +120,20 @@ def test_cpp_host_mirror_passes_the_reference_junit_suite(cli):
     r = subprocess.run([kab.build_mod.HOST_TEST], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("OK")
+
+
+def test_org_json_key_order_prediction():
+    """The emitters print object keys in the iteration order of the java.util.HashMap behind org.json 20131018's
+    JSONObject (default 16 buckets, JDK >= 8 hash spreading h ^ (h >>> 16); no collisions among our keys) — the
+    derivation of SURVEY.md §3.4, recomputed here so the constant order in kassign_host.hpp is not folklore.
+    (Still a prediction: no JVM in the image to confirm it.)"""
+    from oracle import py_oracle as po
+
+    def bucket(key):
+        h = po.java_string_hash(key) & 0xFFFFFFFF
+        return (h ^ (h >> 16)) & 15
+
+    assert sorted(["version", "partitions"], key=bucket) == ["partitions", "version"]                 # KAG:169-171,185
+    assert sorted(["topic", "partition", "replicas"], key=bucket) == ["partition", "replicas", "topic"]  # KAG:178-182
+    assert sorted(["id", "host", "port", "rack"], key=bucket) == ["rack", "port", "host", "id"]        # KAG:117-124
+    assert len({bucket(k) for k in ["topic", "partition", "replicas"]}) == 3 and len({bucket(k) for k in ["id", "host", "port", "rack"]}) == 4

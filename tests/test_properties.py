@@ -77,3 +77,21 @@ def test_invariants_and_three_way_agreement(case_rf):
         out, out_len, fst = ol.fast_run_dense(fctx, np.array([po.java_string_hash(name)], dtype=np.int32), arr, ids, ridx)
         assert fst.code == 0
         assert [[int(x) for x in row] for row in out] == [by_topic[name][p] for p in sorted(cur)]
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(clusters())
+def test_replica_sets_are_a_fixed_point(case_rf):
+    """Re-running the assigner on its own output moves nothing: every replica sticks (loads <= cap, one replica per
+    rack already hold), so the replica SETS are unchanged — only leadership order may differ (fresh Context)."""
+    case, rf = case_rf
+    first = util.run_oracle_case(ol, case)
+    if "error" in first:
+        return
+    by_topic = {}
+    for name, p, reps in first["records"]:
+        by_topic.setdefault(name, {})[p] = reps
+    again = dict(case, topics=[(name, by_topic[name]) for name, _ in case["topics"]])
+    second = util.run_oracle_case(ol, again)
+    assert "records" in second
+    assert [(n, p, sorted(r)) for n, p, r in second["records"]] == [(n, p, sorted(r)) for n, p, r in first["records"]]

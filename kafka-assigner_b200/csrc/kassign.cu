@@ -811,6 +811,7 @@ int32_t ka_last_status(ka_ctx* c, ka_status* st) {
 }
 
 static int validate_dense(ka_ctx* c, int32_t T, int32_t P, int32_t RF, int32_t desired_rf, int32_t S, ka_status* st) {
+    set_status(st, KA_OK);
     if (!c) return set_status(st, KA_ERR_NO_DEVICE);
     if (T < 0 || P < 0 || RF < 0) return set_status(st, KA_ERR_BAD_ARG);
     if (S < 1 || S > KA_MAX_SLOTS) return set_status(st, KA_ERR_LIMIT, -1, -1, S);
@@ -832,7 +833,7 @@ int32_t ka_solve_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     c->staged = false;
     rc = run_dense(c, s, T, P, RF, desired_rf, out_stride, nullptr, nullptr, const_cast<int32_t*>(d_topic_hash),
                    const_cast<int32_t*>(d_cur_broker), d_out_broker, d_out_len, nullptr, nullptr, st);
-    if (rc != KA_OK) return rc;
+    if (rc != KA_OK) { if (st && st->code != rc) set_status(st, rc); return rc; }
     c->last_stream = s;
     c->pending_status = true;
     if (st) return finish_status(c, s, st);
@@ -918,7 +919,7 @@ int32_t ka_solve_dense(ka_ctx* c, int32_t T, const int32_t* topic_hash, int32_t 
     c->staged = false;
     rc = run_dense(c, s, T, P, RF, desired_rf, out_stride, topic_hash, cur_broker, c->d_hash.as<int32_t>(), c->d_cur.as<int32_t>(),
                    c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>(), out_broker, out_len, st);
-    if (rc != KA_OK) return rc;
+    if (rc != KA_OK) { if (st && st->code != rc) set_status(st, rc); return rc; }
     c->last_stream = s;
     c->pending_status = true;
     ka_status local;
@@ -929,6 +930,7 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
                  const int32_t* part_id, const int64_t* rep_off, const int32_t* cur_broker,
                  int32_t desired_rf, int32_t out_stride, int32_t* out_len, int32_t* out_broker,
                  ka_status* st) {
+    set_status(st, KA_OK);
     if (!c) return set_status(st, KA_ERR_NO_DEVICE);
     if (T < 0 || (T > 0 && (!topic_hash || !part_off))) return set_status(st, KA_ERR_BAD_ARG);
     const int S = out_stride;

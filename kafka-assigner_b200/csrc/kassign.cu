@@ -374,7 +374,7 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
         o.out_len = d_out_len;
         o.err_flag = c->d_flags.as<int>() + 1;
         // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide and every extra polling warp costs the
-        // frontier warps issue slots. Measured optimum (tools/phase_times.py, packed-record kernel): 128 threads at
+        // frontier warps issue slots. Measured optimum (tests/tools/phase_times.py, packed-record kernel): 128 threads at
         // N=100, 256 at N=1000, 512 at N=5000, 1024 at N=10000.
         int nt = N < 400 ? 128 : (N < 2500 ? 256 : (N < 7500 ? 512 : 1024));
         if (c->order_threads > 0) nt = c->order_threads;

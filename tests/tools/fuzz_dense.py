@@ -1,6 +1,6 @@
 """Randomised parity fuzz of the DENSE path (ka_solve_dense, incl. the pipelined super-chunk mode) against the CPU
 restatements: the flat-array solver for every case, the structure-faithful oracle for the small ones.
-   KA_PIPELINE_STAGES=3 python tools/fuzz_dense.py --cases 300 --seed 1"""
+   KA_PIPELINE_STAGES=3 python tests/tools/fuzz_dense.py --cases 300 --seed 1"""
 import argparse
 import os
 import random
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import kafka_assigner_b200 as kab  # noqa: E402
 from oracle import oracle_lib as ol  # noqa: E402
 from tests import util  # noqa: E402

@@ -1,12 +1,12 @@
 """Randomised GPU-vs-oracle parity fuzz through the C ABI (ragged ka_solve). Every case must match bit-for-bit: records,
-or the same exception (kind, topic index, partition, operands).   python tools/fuzz_parity.py --cases 4000 --seed 1"""
+or the same exception (kind, topic index, partition, operands).   python tests/tools/fuzz_parity.py --cases 4000 --seed 1"""
 import argparse
 import os
 import random
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import kafka_assigner_b200 as kab  # noqa: E402
 from oracle import oracle_lib as ol  # noqa: E402
 from tests import util  # noqa: E402

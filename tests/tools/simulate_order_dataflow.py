@@ -98,3 +98,43 @@ if __name__ == "__main__":
     for warps, K in [(4, 1), (8, 1), (16, 1), (32, 1), (8, 2), (16, 2), (8, 4)]:
         cyc = simulate(pred, warps, K, iter_cycles=239.0, switch_cycles=250.0, contention=0.35)
         print("  threads=%4d K=%d  -> %.2f M cycles = %.3f ms at 1.965 GHz" % (warps * 32, K, cyc / 1e6, cyc / 1.965e6))
+
+
+def simulate_refill(pred, warps, iter_cycles, contention, refill_overhead=0.10):
+    """Variant: a lane that committed takes the next unassigned partition immediately (no per-window barrier)."""
+    Q = pred.shape[0]
+    commit_time = np.full(Q, np.inf)
+    per_sched = max(1.0, warps / 4.0)
+    period = iter_cycles * (1.0 + contention * (per_sched - 1.0)) * (1.0 + refill_overhead)
+    nxt = 0
+    lanes = [[] for _ in range(warps)]
+    heap = []
+    for w in range(warps):
+        take = list(range(nxt, min(Q, nxt + 32)))
+        nxt += len(take)
+        lanes[w] = take
+        heapq.heappush(heap, (0.0, w))
+    t_end = 0.0
+    while heap:
+        t, w = heapq.heappop(heap)
+        if not lanes[w]:
+            continue
+        still = []
+        for q in lanes[w]:
+            ok = True
+            for p in pred[q]:
+                if p >= 0 and not (commit_time[p] <= t):
+                    ok = False
+                    break
+            if ok:
+                commit_time[q] = t + period
+            else:
+                still.append(q)
+        free = 32 - len(still)
+        take = list(range(nxt, min(Q, nxt + free)))
+        nxt += len(take)
+        lanes[w] = still + take
+        t_end = max(t_end, t + period)
+        if lanes[w]:
+            heapq.heappush(heap, (t + period, w))
+    return t_end

@@ -2,7 +2,8 @@
 //
 // Reference boundary: KafkaTopicAssigner.generateAssignment (KafkaTopicAssigner.java:42-72) batched over
 // the topic loop of KafkaAssignmentGenerator.java:172-184. No CPU fallback exists in this library.
-#include "kassign_kernels.cuh"
+#include "kassign_stage.cuh"
+#include "kassign_order.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -72,8 +73,8 @@ struct ka_ctx {
     // counters of brokers not in the current table (Context.counter is keyed by broker id)
     std::unordered_map<int32_t, std::vector<int32_t>> parked;
     // scratch
-    DevBuf d_hash, d_part_off, d_rep_off, d_cur, d_set, d_meta, d_ticket, d_out, d_out_len, d_hist, d_tstatus, d_flags;
-    DevBuf d_tick4, d_idx01, d_pcode;
+    DevBuf d_hash, d_part_off, d_rep_off, d_cur, d_out, d_out_len, d_tstatus, d_flags;
+    DevBuf d_rec, d_perm, d_ntl, d_loff, d_lend, d_lvl_end;  // records, chosen positions, schedule permutation, level tables
     HostPinned* h_pin = nullptr;
     // bookkeeping
     bool timing = false;
@@ -88,7 +89,6 @@ struct ka_ctx {
     cudaEvent_t ev_in = nullptr, ev_stage[8] = {};
     cudaEvent_t ev_pipe[8][5] = {};
     int last_stages = 1;
-    DevBuf d_seed;
     // staged problem (between the context-free stage and the leader-order stage)
     bool staged = false;
     struct StagedBlock* staged_block = nullptr;  // StageDesc of ka_stage_dense_device, consumed by ka_order_device
@@ -142,21 +142,24 @@ int park_counters(ka_ctx* c) {
 
 struct Plan {
     // kernel A
-    int a_warps, a_grid, a_load_bytes, a_slab_bytes, a_cnt_bytes, a_load_kind;  // kind 0=u8 1=u16 2=u32
+    int a_warps, a_load_bytes, a_slab_bytes, a_cnt_bytes, a_load_kind;  // kind 0=u8 1=u16 2=u32
     int a_rackptr, a_rp_bytes;
+    int a_levels;                                   // 1: some topic may hold a broker twice -> conflict levels + tables
+    int lv_owner_bytes, lv_last_bytes, lv_p_bytes;  // per-warp scratch of the level pass
     size_t a_smem;
-    // tickets
-    int64_t L;
-    int num_chunks;
-    int t_warps_hist, t_warps_rank, t_grid_hist, t_grid_rank;
-    size_t t_smem_hist, t_smem_rank;
-    // order
-    int RS;
+    // leader order
+    int rec_kind, rec_bytes;  // 3: 16 B records (rows <= 3), 4 / 8: 32 B records (rows of 4 / 5..8)
+    int b_gctr;               // counters stay in global memory (table too large for shared memory)
+    int b_ring_log2;          // log2(records per TMA ring stage)
+    int b_threads;
     size_t b_smem;
 };
 
-int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, Plan& pl, ka_status* st) {
+constexpr size_t KA_ORDER_SMEM_BUDGET = 226 * 1024;
+
+int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, bool ragged, Plan& pl, ka_status* st) {
     const int N = c->N;
+    if (Q >= (int64_t)1 << 31) return set_status(st, KA_ERR_LIMIT, -1, -1, INT_MAX, 0);
     // ---- kernel A
     pl.a_load_kind = capmax <= 255 ? 0 : (capmax <= 65535 ? 1 : 2);
     const int lsz = pl.a_load_kind == 0 ? 1 : (pl.a_load_kind == 1 ? 2 : 4);
@@ -169,37 +172,49 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, Plan& pl, k
     pl.a_rackptr = 0;
     if (const char* e = std::getenv("KA_SPREAD_RACKPTR")) pl.a_rackptr = std::atoi(e) && c->R > 0 && c->R <= 4096;
     pl.a_rp_bytes = pl.a_rackptr ? (int)align16((size_t)c->R * 2) : 0;
-    const size_t per_warp = (size_t)pl.a_load_bytes + pl.a_slab_bytes + pl.a_cnt_bytes + 3 * (size_t)pl.a_rp_bytes;
+    // capacity 1 == every broker holds at most one partition of a topic == the topic is a single conflict level
+    pl.a_levels = (capmax > 1 || ragged) ? 1 : 0;
+    if (const char* e = std::getenv("KA_FORCE_LEVELS")) pl.a_levels = pl.a_levels || std::atoi(e);
+    pl.lv_owner_bytes = pl.a_levels ? (int)align16((size_t)std::max(N, 1) * 4) : 0;
+    pl.lv_last_bytes = pl.a_levels ? (int)align16((size_t)std::max(N, 1) * 2) : 0;
+    pl.lv_p_bytes = pl.a_levels ? (int)align16((size_t)(std::max(Pmax, 1) + 2) * 2) : 0;
+    const size_t per_warp = (size_t)pl.a_load_bytes + pl.a_slab_bytes + pl.a_cnt_bytes + 3 * (size_t)pl.a_rp_bytes +
+                            pl.lv_owner_bytes + pl.lv_last_bytes + 2 * (size_t)pl.lv_p_bytes;
     const size_t shared = 16 + (size_t)c->blob_bytes;
     if (shared + per_warp > KA_SMEM_BUDGET) return set_status(st, KA_ERR_LIMIT, -1, -1, Pmax, N);
     pl.a_warps = (int)std::min<size_t>(16, (KA_SMEM_BUDGET - shared) / per_warp);
-    // prefer >= 2 CTAs/SM when the table is small: cap warps so that two CTAs fit
     pl.a_smem = shared + per_warp * pl.a_warps;
-    // ---- tickets
-    const int64_t windows = (Q + 31) / 32;
-    const size_t hist_pw = (size_t)std::max(N, 1) * 4, rank_pw = hist_pw * 2;
-    if (rank_pw > KA_SMEM_BUDGET) return set_status(st, KA_ERR_LIMIT, -1, -1, N, 0);
-    pl.t_warps_hist = (int)std::max<size_t>(1, std::min<size_t>(32, KA_SMEM_BUDGET / hist_pw));
-    pl.t_warps_rank = (int)std::max<size_t>(1, std::min<size_t>(32, KA_SMEM_BUDGET / rank_pw));
-    const int64_t max_conc = (int64_t)c->sm_count * pl.t_warps_rank;
-    // chunks: enough to fill the machine with short in-order rank walks (~8 windows each); the scan is a warp-per-broker
-    // shuffle scan whose cost is its (strided) traffic chunks x N x 4 B — keep that to a few MB (measured: C5 regresses
-    // beyond it) and within KA_SCAN_MAX_CHUNKS.
-    int64_t nc = (std::max<int64_t>(windows, 1) + 7) / 8;
-    nc = std::min<int64_t>(nc, std::min<int64_t>(KA_SCAN_MAX_CHUNKS, std::max<int64_t>(64, 3500000 / std::max(N, 1))));
-    (void)max_conc;
-    nc = std::max<int64_t>(1, std::min<int64_t>(nc, std::max<int64_t>(windows, 1)));
-    int64_t wpc = (std::max<int64_t>(windows, 1) + nc - 1) / nc;  // windows per chunk
-    pl.L = wpc * 32;
-    pl.num_chunks = (int)((std::max<int64_t>(windows, 1) + wpc - 1) / wpc);
-    pl.t_smem_hist = hist_pw * pl.t_warps_hist;
-    pl.t_smem_rank = rank_pw * pl.t_warps_rank;
-    pl.t_grid_hist = (pl.num_chunks + pl.t_warps_hist - 1) / pl.t_warps_hist;
-    pl.t_grid_rank = (pl.num_chunks + pl.t_warps_rank - 1) / pl.t_warps_rank;
-    // ---- order
-    pl.RS = S <= 4 ? 4 : 8;
-    pl.b_smem = (size_t)std::max(N, 1) * pl.RS * 4;
-    if (pl.b_smem > 220 * 1024) return set_status(st, KA_ERR_LIMIT, -1, -1, N, pl.RS);
+    // ---- leader order
+    pl.rec_kind = S <= 3 ? 3 : (S == 4 ? 4 : 8);
+    pl.rec_bytes = pl.rec_kind == 3 ? 16 : 32;
+    const int cw = pl.rec_kind == 8 ? 8 : 4;
+    const int max_nt = pl.rec_kind == 3 ? 992 : (pl.rec_kind == 4 ? 480 : 224);  // + the producer warp <= 1024 / 512 / 256 threads
+    const size_t ctr_bytes = (size_t)(std::max(N, 1) + 1) * cw * 4;  // + the dummy row that pads rows shorter than 3
+    // record ring: KA_RING_STAGES stages of 2^lg records, as large as fits next to the counter table (<= 128 KB)
+    const int lg_max = pl.rec_kind == 3 ? 10 : 9, lg_min = 7;
+    auto ring_bytes = [&](int l) { return ((size_t)KA_RING_STAGES << l) * pl.rec_bytes + 256; };
+    int lg = lg_max;
+    pl.b_gctr = 0;
+    while (lg > lg_min && ctr_bytes + ring_bytes(lg) > KA_ORDER_SMEM_BUDGET) --lg;
+    if (ctr_bytes + ring_bytes(lg) > KA_ORDER_SMEM_BUDGET) {
+        pl.b_gctr = 1;  // counter table beyond shared memory: rows stay in global memory (L2)
+        lg = lg_max;
+    }
+    if (const char* e = std::getenv("KA_ORDER_GLOBAL_CTR")) pl.b_gctr = pl.b_gctr || std::atoi(e);
+    pl.b_ring_log2 = lg;
+    pl.b_smem = ring_bytes(lg) + (pl.b_gctr ? 0 : ctr_bytes);
+    // CTA size ~ level width: a level is one pass of the CTA. Capacity 1: level = topic (P wide). Otherwise a level
+    // holds each broker at most once, i.e. at most N / S partitions; measured widths are about half of that.
+    int64_t width = pl.a_levels ? std::min<int64_t>(Pmax, std::max<int64_t>(1, N / std::max(S, 1) / 2)) : Pmax;
+    // a level wider than the CTA is cut into equal chunks (the kernel is issue-bound there: equal halves cost nothing)
+    const int64_t cuts = (std::max<int64_t>(width, 1) + max_nt - 1) / max_nt;
+    width = (std::max<int64_t>(width, 1) + cuts - 1) / cuts;
+    int nt = (int)std::min<int64_t>(max_nt, ((width + 31) / 32) * 32);
+    if (c->order_threads > 0) nt = c->order_threads;
+    if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
+    nt = std::max(32, std::min(max_nt, (nt / 32) * 32));
+    nt = std::min(nt, (KA_RING_STAGES - 1) << lg);
+    pl.b_threads = nt;
     return KA_OK;
 }
 
@@ -220,6 +235,7 @@ struct StageDesc {
     int desired_rf = -1, S = 1, Pmax = 0;
     int64_t capmax = 0;
     int64_t q0 = 0;                 // first partition row of the block inside the ctx scratch arrays
+    int blk = 0;                    // ordinal of the block inside a pipelined solve (its level tables: loff at topic_base + blk)
     Plan pl;
 };
 
@@ -227,22 +243,22 @@ struct StageDesc {
 struct StagedBlock { StageDesc d; };
 namespace {
 
-int reserve_scratch(ka_ctx* c, int64_t Qtot, int S, int Ttot, int max_chunks) {
-    const int N = c->N;
-    KA_CUDA(c->d_set.reserve((size_t)std::max<int64_t>(Qtot, 1) * S * 4));
-    KA_CUDA(c->d_meta.reserve((size_t)std::max<int64_t>(Qtot, 1) * 4));
-    KA_CUDA(c->d_ticket.reserve((size_t)std::max<int64_t>(Qtot, 1) * S * 4));
-    KA_CUDA(c->d_tick4.reserve((size_t)std::max<int64_t>(Qtot, 1) * 16));
-    KA_CUDA(c->d_idx01.reserve((size_t)std::max<int64_t>(Qtot, 1) * 4));
-    KA_CUDA(c->d_pcode.reserve((size_t)std::max<int64_t>(Qtot, 1)));
-    KA_CUDA(c->d_hist.reserve((size_t)std::max(max_chunks, 1) * std::max(N, 1) * 4));
-    KA_CUDA(c->d_seed.reserve((size_t)std::max(N, 1) * 4));
+int reserve_scratch(ka_ctx* c, int64_t Qtot, int rec_bytes, int Ttot, int blocks, bool levels) {
+    const size_t q = (size_t)std::max<int64_t>(Qtot, 1);
+    KA_CUDA(c->d_rec.reserve(q * rec_bytes + 256));
+    if (levels) {
+        KA_CUDA(c->d_perm.reserve(q * 2));
+        KA_CUDA(c->d_lend.reserve(q * 4));
+        KA_CUDA(c->d_lvl_end.reserve(q * 4));
+        KA_CUDA(c->d_ntl.reserve((size_t)std::max(Ttot, 1) * 4));
+        KA_CUDA(c->d_loff.reserve((size_t)(std::max(Ttot, 1) + blocks + 1) * 4));
+    }
     KA_CUDA(c->d_tstatus.reserve((size_t)std::max(Ttot, 1) * sizeof(int4)));
     KA_CUDA(c->d_flags.reserve(64));
     return KA_OK;
 }
 
-// flags: [0] lowest failing topic (unsigned atomicMin, 0xFFFFFFFF = none), [1] spin guard (0xFFFFFFFF = not tripped)
+// flags: [0] lowest failing topic (unsigned atomicMin, 0xFFFFFFFF = none)
 int reset_flags(ka_ctx* c, cudaStream_t s) {
     c->h_pin->err_topic = -1;
     c->h_pin->spin_flag = -1;
@@ -250,8 +266,23 @@ int reset_flags(ka_ctx* c, cudaStream_t s) {
     return KA_OK;
 }
 
-// Context-free part of a block (shards across GPUs): kernel A + per-chunk broker histograms.
-int enq_sticky_hist(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
+template <typename LoadT, bool LEVELS>
+cudaError_t launch_stage(ka_ctx* c, cudaStream_t s, const KaSolveParams& p, const Plan& pl, int T) {
+    auto kern = ka_sticky_spread_kernel<LoadT, LEVELS>;
+    const int threads = pl.a_warps * 32;
+    cudaError_t e = allow_smem(kern, pl.a_smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, pl.a_smem);
+    if (e != cudaSuccess) return e;
+    int grid = (T + pl.a_warps - 1) / pl.a_warps;
+    grid = std::min(grid, std::max(1, occ) * c->sm_count);
+    kern<<<grid, threads, pl.a_smem, s>>>(p, pl.a_load_bytes, pl.a_slab_bytes, pl.a_cnt_bytes, pl.lv_owner_bytes, pl.lv_last_bytes, pl.lv_p_bytes);
+    return cudaGetLastError();
+}
+
+// Context-free part of a block (shards across GPUs): kernel A (records in schedule order) + the level tables.
+int enq_stage(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
     const int N = c->N, S = d.S;
     const Plan& pl = d.pl;
     if (d.T > 0) {
@@ -281,139 +312,100 @@ int enq_sticky_hist(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
         p.range = c->range;
         p.glut = c->d_glut.as<uint16_t>();
         p.broker_id = c->d_broker_id.as<int32_t>();
-        p.set = c->d_set.as<int32_t>() + d.q0 * S;
-        p.meta = c->d_meta.as<uint32_t>() + d.q0;
+        p.rec_kind = pl.rec_kind;
+        p.rec = c->d_rec.as<unsigned char>() + (size_t)d.q0 * pl.rec_bytes;
+        p.perm = pl.a_levels ? c->d_perm.as<uint16_t>() + d.q0 : nullptr;
+        p.chunk_w = pl.b_threads;
+        p.ntl = pl.a_levels ? c->d_ntl.as<int32_t>() + d.topic_base : nullptr;
+        p.lend = pl.a_levels ? c->d_lend.as<uint32_t>() + d.q0 : nullptr;
         p.tstatus = c->d_tstatus.as<int4>();
         p.err_topic = c->d_flags.as<unsigned>();
-        const int threads = pl.a_warps * 32;
-        int grid = (d.T + pl.a_warps - 1) / pl.a_warps;
-        int occ = 1;
         cudaError_t e;
-        if (pl.a_load_kind == 0) {
-            e = allow_smem(ka_sticky_spread_kernel<uint8_t>, pl.a_smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ka_sticky_spread_kernel<uint8_t>, threads, pl.a_smem);
-        } else if (pl.a_load_kind == 1) {
-            e = allow_smem(ka_sticky_spread_kernel<uint16_t>, pl.a_smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ka_sticky_spread_kernel<uint16_t>, threads, pl.a_smem);
+        if (pl.a_levels) {
+            if (pl.a_load_kind == 0) e = launch_stage<uint8_t, true>(c, s, p, pl, d.T);
+            else if (pl.a_load_kind == 1) e = launch_stage<uint16_t, true>(c, s, p, pl, d.T);
+            else e = launch_stage<uint32_t, true>(c, s, p, pl, d.T);
         } else {
-            e = allow_smem(ka_sticky_spread_kernel<uint32_t>, pl.a_smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ka_sticky_spread_kernel<uint32_t>, threads, pl.a_smem);
+            if (pl.a_load_kind == 0) e = launch_stage<uint8_t, false>(c, s, p, pl, d.T);
+            else if (pl.a_load_kind == 1) e = launch_stage<uint16_t, false>(c, s, p, pl, d.T);
+            else e = launch_stage<uint32_t, false>(c, s, p, pl, d.T);
         }
         KA_CUDA(e);
-        grid = std::min(grid, std::max(1, occ) * c->sm_count);
-        if (pl.a_load_kind == 0)
-            ka_sticky_spread_kernel<uint8_t><<<grid, threads, pl.a_smem, s>>>(p, pl.a_load_bytes, pl.a_slab_bytes, pl.a_cnt_bytes);
-        else if (pl.a_load_kind == 1)
-            ka_sticky_spread_kernel<uint16_t><<<grid, threads, pl.a_smem, s>>>(p, pl.a_load_bytes, pl.a_slab_bytes, pl.a_cnt_bytes);
-        else
-            ka_sticky_spread_kernel<uint32_t><<<grid, threads, pl.a_smem, s>>>(p, pl.a_load_bytes, pl.a_slab_bytes, pl.a_cnt_bytes);
-        KA_CUDA(cudaGetLastError());
         c->launches++;
     }
     if (c->timing && c->ev_mark) KA_CUDA(cudaEventRecord(c->ev_mark, s));  // end of kernel A
-    if (d.Q > 0 && N > 0) {
-        KA_CUDA(allow_smem(ka_ticket_hist_kernel, pl.t_smem_hist));
-        ka_ticket_hist_kernel<<<pl.t_grid_hist, pl.t_warps_hist * 32, pl.t_smem_hist, s>>>(c->d_set.as<int32_t>() + d.q0 * S, d.Q, S, N, pl.L,
-                                                                                            pl.num_chunks, c->d_hist.as<int32_t>());
+    if (pl.a_levels && d.T > 0) {
+        int32_t* ntl = c->d_ntl.as<int32_t>() + d.topic_base;
+        int32_t* loff = c->d_loff.as<int32_t>() + d.topic_base + d.blk;  // every block keeps T_k + 1 entries
+        ka_level_scan_kernel<<<1, 1024, 0, s>>>(ntl, d.T, loff);
         KA_CUDA(cudaGetLastError());
-        c->launches++;
-    }
-    return KA_OK;
-}
-
-inline bool use_packed(const StageDesc& d) {
-    int spec = 1;
-    if (const char* e = std::getenv("KA_ORDER_SPEC")) spec = std::atoi(e);
-    return d.pl.RS == 4 && d.S <= 3 && spec;  // rows of <= 3 replicas: packed records + emit kernel
-}
-
-// seed[b] = current counter-row sum: the ticket base of the first block of a solve
-int enq_seed_init(ka_ctx* c, cudaStream_t s, int RS) {
-    if (c->N > 0) {
-        ka_seed_init_kernel<<<(c->N + 255) / 256, 256, 0, s>>>(c->d_ctr8.as<int32_t>(), RS, c->N, c->d_seed.as<int32_t>());
-        KA_CUDA(cudaGetLastError());
-        c->launches++;
-    }
-    return KA_OK;
-}
-
-// Tickets of a block: exclusive scan of the chunk histograms (seed in -> seed + block totals out) and in-order ranks.
-int enq_tickets(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
-    const int N = c->N, S = d.S;
-    const Plan& pl = d.pl;
-    if (d.Q > 0 && N > 0) {
-        const bool packed = use_packed(d);
-        KA_CUDA(allow_smem(ka_ticket_rank_kernel, pl.t_smem_rank));
-        ka_ticket_scan_kernel<<<(N + 7) / 8, 256, 0, s>>>(c->d_hist.as<int32_t>(), pl.num_chunks, N, c->d_seed.as<int32_t>());
-        KA_CUDA(cudaGetLastError());
-        ka_ticket_rank_kernel<<<pl.t_grid_rank, pl.t_warps_rank * 32, pl.t_smem_rank, s>>>(
-            c->d_set.as<int32_t>() + d.q0 * S, d.Q, S, N, pl.L, pl.num_chunks, c->d_hist.as<int32_t>(), c->d_ticket.as<int32_t>() + d.q0 * S,
-            c->d_meta.as<uint32_t>() + d.q0, packed ? c->d_tick4.as<int4>() + d.q0 : nullptr, packed ? c->d_idx01.as<uint32_t>() + d.q0 : nullptr);
+        ka_level_fill_kernel<<<(d.T + 7) / 8, 256, 0, s>>>(ntl, loff, c->d_lend.as<uint32_t>() + d.q0, d.d_part_off, d.P, d.T,
+                                                            c->d_lvl_end.as<uint32_t>() + d.q0);
         KA_CUDA(cudaGetLastError());
         c->launches += 2;
     }
     return KA_OK;
 }
 
+template <int RS, int MAXNT, bool GCTR, bool SINGLE, bool WARP1>
+cudaError_t launch_order_t(cudaStream_t s, const KaOrderParams& o, const Plan& pl) {
+    auto kern = ka_order_levels_kernel<RS, GCTR, MAXNT, SINGLE, WARP1>;
+    cudaError_t e = allow_smem(kern, pl.b_smem);
+    if (e != cudaSuccess) return e;
+    kern<<<1, pl.b_threads + 32, pl.b_smem, s>>>(o);
+    return cudaGetLastError();
+}
+
+template <int RS, int MAXNT>
+cudaError_t launch_order(cudaStream_t s, const KaOrderParams& o, const Plan& pl) {
+    if constexpr (RS != 3) {
+        return pl.b_gctr ? launch_order_t<RS, MAXNT, true, false, false>(s, o, pl) : launch_order_t<RS, MAXNT, false, false, false>(s, o, pl);
+    } else {
+    // rows <= 3: chunk arithmetic (one chunk per topic?) and barrier flavour (single consumer warp?) are compile-time
+    const bool single = o.uniform_width != 0 && o.uniform_width <= (uint32_t)pl.b_threads, warp1 = pl.b_threads == 32;
+    const int sel = (pl.b_gctr ? 4 : 0) | (single ? 2 : 0) | (warp1 ? 1 : 0);
+    switch (sel) {
+        case 0: return launch_order_t<3, MAXNT, false, false, false>(s, o, pl);
+        case 1: return launch_order_t<3, MAXNT, false, false, true>(s, o, pl);
+        case 2: return launch_order_t<3, MAXNT, false, true, false>(s, o, pl);
+        case 3: return launch_order_t<3, MAXNT, false, true, true>(s, o, pl);
+        case 4: return launch_order_t<3, MAXNT, true, false, false>(s, o, pl);
+        case 5: return launch_order_t<3, MAXNT, true, false, true>(s, o, pl);
+        case 6: return launch_order_t<3, MAXNT, true, true, false>(s, o, pl);
+        default: return launch_order_t<3, MAXNT, true, true, true>(s, o, pl);
+    }
+    }
+}
+
 // The serial chain through Context.counter (KAS:202-239) for a block + the parallel emit. d_out/d_out_len: block's rows.
 int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out, int32_t* d_out_len) {
     const int N = c->N, S = d.S;
     const int64_t Q = d.Q;
+    const Plan& pl = d.pl;
     if (Q > 0 && N > 0) {
-        const bool packed = use_packed(d);
         KaOrderParams o{};
-        o.Q = Q;
-        o.S = S;
+        o.Q = (uint32_t)Q;
         o.N = N;
-        o.set = c->d_set.as<int32_t>() + d.q0 * S;
-        o.ticket = c->d_ticket.as<int32_t>() + d.q0 * S;
-        o.meta = c->d_meta.as<uint32_t>() + d.q0;
-        o.broker_id = c->d_broker_id.as<int32_t>();
+        o.S = S;
+        o.rec = c->d_rec.as<unsigned char>() + (size_t)d.q0 * pl.rec_bytes;
+        o.uniform_width = pl.a_levels ? 0u : (uint32_t)d.P;
+        o.chunk_end = pl.a_levels ? c->d_lvl_end.as<uint32_t>() + d.q0 : nullptr;
+        o.nchunk_ptr = pl.a_levels ? c->d_loff.as<int32_t>() + d.topic_base + d.blk + d.T : nullptr;
         o.ctr8 = c->d_ctr8.as<int32_t>();
+        o.broker_id = c->d_broker_id.as<int32_t>();
         o.out = d_out;
         o.out_len = d_out_len;
-        o.err_flag = c->d_flags.as<int>() + 1;
-        // CTA size of the leader-order kernel: the dependency DAG is ~N/RF wide and every extra polling warp costs the
-        // frontier warps issue slots. Measured optimum (tests/tools/phase_times.py, packed-record kernel): 128 threads at
-        // N=100, 256 at N=1000, 512 at N=5000, 1024 at N=10000.
-        int nt = N < 400 ? 128 : (N < 2500 ? 256 : (N < 7500 ? 512 : 1024));
-        if (c->order_threads > 0) nt = c->order_threads;
-        if (const char* e = std::getenv("KA_ORDER_THREADS")) nt = std::atoi(e);
-        o.tick4 = c->d_tick4.as<int4>() + d.q0;
-        o.idx01 = c->d_idx01.as<uint32_t>() + d.q0;
-        o.pcode = c->d_pcode.as<uint8_t>() + d.q0;
-        const size_t b_smem = d.pl.b_smem;
-        if (packed) {
-#define KA_LAUNCH_ORDER3(NT)                                                        \
-    do {                                                                            \
-        KA_CUDA(allow_smem(ka_leader_order3_kernel<NT>, b_smem));                   \
-        ka_leader_order3_kernel<NT><<<1, NT, b_smem, s>>>(o);                       \
-    } while (0)
-            if (nt >= 1024) KA_LAUNCH_ORDER3(1024);
-            else if (nt >= 512) KA_LAUNCH_ORDER3(512);
-            else if (nt >= 256) KA_LAUNCH_ORDER3(256);
-            else if (nt >= 128) KA_LAUNCH_ORDER3(128);
-            else KA_LAUNCH_ORDER3(64);
-#undef KA_LAUNCH_ORDER3
-        } else if (d.pl.RS == 4) {
-#define KA_LAUNCH_ORDER4(NT)                                                        \
-    do {                                                                            \
-        KA_CUDA(allow_smem(ka_leader_order4_kernel<NT>, b_smem));                   \
-        ka_leader_order4_kernel<NT><<<1, NT, b_smem, s>>>(o);                       \
-    } while (0)
-            if (nt >= 1024) KA_LAUNCH_ORDER4(1024);
-            else if (nt >= 512) KA_LAUNCH_ORDER4(512);
-            else if (nt >= 256) KA_LAUNCH_ORDER4(256);
-            else KA_LAUNCH_ORDER4(128);
-#undef KA_LAUNCH_ORDER4
-        } else {
-            KA_CUDA(allow_smem(ka_leader_order_kernel<8, 256>, b_smem));
-            ka_leader_order_kernel<8, 256><<<1, 256, b_smem, s>>>(o);
-        }
-        KA_CUDA(cudaGetLastError());
+        o.ring_log2 = pl.b_ring_log2;
+        cudaError_t e;
+        if (pl.rec_kind == 3) e = launch_order<3, 992>(s, o, pl);
+        else if (pl.rec_kind == 4) e = launch_order<4, 480>(s, o, pl);
+        else e = launch_order<8, 224>(s, o, pl);
+        KA_CUDA(e);
         c->launches++;
-        if (packed) {
-            ka_emit_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(o.set, o.meta, o.pcode, c->d_broker_id.as<int32_t>(), Q, S, d_out, d_out_len);
+        if (pl.rec_kind == 3) {
+            ka_emit3_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(o.rec),
+                                                                        pl.a_levels ? c->d_perm.as<uint16_t>() + d.q0 : nullptr, d.d_part_off, d.T,
+                                                                        d.P, c->d_broker_id.as<int32_t>(), (uint32_t)Q, S, d_out, d_out_len);
             KA_CUDA(cudaGetLastError());
             c->launches++;
         }
@@ -436,10 +428,9 @@ int pipeline_stages(int T, int64_t Q) {
     return std::max(1, std::min(k, std::min(8, std::max(T, 1))));
 }
 
-// Whole dense solve on `s_main`, pipelined in K topic super-chunks: the aux stream runs (H2D,) kernel A and the ticket
-// kernels of chunk k+1 while s_main runs the leader-order chain of chunk k (and the D2H of its output). Tickets stay
-// exact: chunk k's seed is the previous seed plus the previous chunk's broker totals (ka_ticket_scan_kernel), and
-// s_main orders the chunks strictly one after the other through the counters in ctr8.
+// Whole dense solve on `s_main`, pipelined in K topic super-chunks: the aux stream runs (H2D,) kernel A and the level
+// tables of chunk k+1 while s_main runs the leader-order chain of chunk k (and the D2H of its output); s_main orders the
+// chunks strictly one after the other through the counters in ctr8.
 // h_* non-null = host-buffer form (copies inside); d_* always valid device buffers of the full problem.
 int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_rf, int S, const int32_t* h_hash, const int32_t* h_cur,
               int32_t* d_hash, int32_t* d_cur, int32_t* d_out, int32_t* d_out_len, int32_t* h_out, int32_t* h_out_len, ka_status* st) {
@@ -448,7 +439,6 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
     const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
     const int K = pipeline_stages(T, Q);
     StageDesc ds[8];
-    int max_chunks = 1;
     for (int k = 0; k < K; ++k) {
         const int t0 = (int)((int64_t)T * k / K), t1 = (int)((int64_t)T * (k + 1) / K);
         StageDesc& d = ds[k];
@@ -464,11 +454,11 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
         d.S = S;
         d.Pmax = P;
         d.capmax = capmax;
-        int rc = make_plan(c, d.Q, S, P, capmax, d.pl, st);
+        d.blk = k;
+        int rc = make_plan(c, d.Q, S, P, capmax, false, d.pl, st);
         if (rc != KA_OK) return rc;
-        max_chunks = std::max(max_chunks, d.pl.num_chunks);
     }
-    int rc = reserve_scratch(c, Q, S, T, max_chunks);
+    int rc = reserve_scratch(c, Q, ds[0].pl.rec_bytes, T, K, ds[0].pl.a_levels != 0);
     if (rc != KA_OK) return set_status(st, rc);
     c->last_stages = K;
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[0], s_main));
@@ -480,10 +470,8 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
         if ((rc = reset_flags(c, s)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev[1], s));
         c->ev_mark = c->ev[2];
-        if ((rc = enq_sticky_hist(c, s, d)) != KA_OK) return rc;
+        if ((rc = enq_stage(c, s, d)) != KA_OK) return rc;
         c->ev_mark = nullptr;
-        if ((rc = enq_seed_init(c, s, d.pl.RS)) != KA_OK) return rc;
-        if ((rc = enq_tickets(c, s, d)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
         if ((rc = enq_order_emit(c, s, d, d_out, d_out_len)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
@@ -496,7 +484,6 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
         KA_CUDA(cudaEventRecord(c->ev_in, s_main));           // inputs ready / earlier work on s_main done
         KA_CUDA(cudaStreamWaitEvent(aux, c->ev_in, 0));
         if ((rc = reset_flags(c, aux)) != KA_OK) return rc;
-        if ((rc = enq_seed_init(c, aux, ds[0].pl.RS)) != KA_OK) return rc;
         for (int k = 0; k < K; ++k) {
             StageDesc& d = ds[k];
             if (h_hash && d.T > 0) KA_CUDA(cudaMemcpyAsync(d_hash + d.topic_base, h_hash + d.topic_base, (size_t)d.T * 4, cudaMemcpyHostToDevice, aux));
@@ -504,9 +491,8 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
                 KA_CUDA(cudaMemcpyAsync(d_cur + d.q0 * RF, h_cur + d.q0 * RF, (size_t)d.Q * RF * 4, cudaMemcpyHostToDevice, aux));
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][0], aux));
             c->ev_mark = c->timing ? c->ev_pipe[k][1] : nullptr;
-            if ((rc = enq_sticky_hist(c, aux, d)) != KA_OK) return rc;
+            if ((rc = enq_stage(c, aux, d)) != KA_OK) return rc;
             c->ev_mark = nullptr;
-            if ((rc = enq_tickets(c, aux, d)) != KA_OK) return rc;
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][2], aux));
             KA_CUDA(cudaEventRecord(c->ev_stage[k], aux));
             KA_CUDA(cudaStreamWaitEvent(s_main, c->ev_stage[k], 0));
@@ -542,9 +528,6 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
         if (ord >= 0 && c->last_part_id && c->last_part_off) r.partition = c->last_part_id[c->last_part_off[t] + ord];
         r.a = c->h_pin->tstatus.z;
         r.b = c->h_pin->tstatus.w;
-    } else if (c->h_pin->spin_flag != -1) {
-        r.code = KA_ERR_CUDA;
-        std::fprintf(stderr, "[kassign] internal error: leader-order dataflow guard tripped\n");
     }
     if (c->timing && c->ev_valid) {
         for (int i = 0; i < 8; ++i) c->last_ms[i] = 0.f;
@@ -552,7 +535,7 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
         if (c->last_stages <= 1) {
             cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]);  // H2D
             cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]);  // kernel A
-            cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);  // tickets (hist + seed + scan + rank)
+            cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);  // level tables (scan + fill; absent when capacity is 1)
             cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);  // kernel B + emit
             cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);  // D2H
         } else {  // pipelined: phases of different chunks overlap; report the per-phase sums
@@ -645,8 +628,8 @@ void ka_ctx_destroy(ka_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_blob, &c->d_glut, &c->d_broker_id, &c->d_ctr8, &c->d_hash, &c->d_part_off, &c->d_rep_off, &c->d_cur, &c->d_set,
-                      &c->d_meta, &c->d_ticket, &c->d_tick4, &c->d_idx01, &c->d_pcode, &c->d_seed, &c->d_out, &c->d_out_len, &c->d_hist, &c->d_tstatus, &c->d_flags})
+    for (DevBuf* b : {&c->d_blob, &c->d_glut, &c->d_broker_id, &c->d_ctr8, &c->d_hash, &c->d_part_off, &c->d_rep_off, &c->d_cur, &c->d_rec,
+                      &c->d_perm, &c->d_ntl, &c->d_loff, &c->d_lend, &c->d_lvl_end, &c->d_out, &c->d_out_len, &c->d_tstatus, &c->d_flags})
         b->release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -739,7 +722,7 @@ int32_t ka_ctx_set_brokers(ka_ctx* c, int32_t N, const int32_t* broker_id, const
     KA_CUDA(c->d_broker_id.reserve((size_t)std::max(N, 1) * 4));
     if (N > 0) KA_CUDA(cudaMemcpy(c->d_broker_id.p, broker_id, (size_t)N * 4, cudaMemcpyHostToDevice));
     // counters for the new table
-    std::vector<int32_t> h((size_t)std::max(N, 1) * KA_MAX_SLOTS, 0);
+    std::vector<int32_t> h((size_t)(std::max(N, 1) + 1) * KA_MAX_SLOTS, 0);  // + the order kernel's dummy row (index N)
     for (int i = 0; i < N; ++i) {
         auto it = c->parked.find(broker_id[i]);
         if (it != c->parked.end()) std::copy(it->second.begin(), it->second.end(), h.begin() + (size_t)i * KA_MAX_SLOTS);
@@ -863,16 +846,16 @@ int32_t ka_stage_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     const int rf_t = desired_rf >= 0 ? desired_rf : RF;
     d.capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
     c->staged = false;
-    rc = make_plan(c, d.Q, d.S, d.Pmax, d.capmax, d.pl, &lst);
+    rc = make_plan(c, d.Q, d.S, d.Pmax, d.capmax, false, d.pl, &lst);
     if (rc != KA_OK) return rc;
-    if ((rc = reserve_scratch(c, d.Q, d.S, T, d.pl.num_chunks)) != KA_OK) return rc;
+    if ((rc = reserve_scratch(c, d.Q, d.pl.rec_bytes, T, 1, d.pl.a_levels != 0)) != KA_OK) return rc;
     c->last_part_id = nullptr;
     c->last_part_off = nullptr;
     c->last_stages = 1;
     if (c->timing) { cudaEventRecord(c->ev[0], s); cudaEventRecord(c->ev[1], s); }
     if ((rc = reset_flags(c, s)) != KA_OK) return rc;
     c->ev_mark = c->timing ? c->ev[2] : nullptr;
-    rc = enq_sticky_hist(c, s, d);
+    rc = enq_stage(c, s, d);
     c->ev_mark = nullptr;
     if (rc != KA_OK) return rc;
     c->staged = true;
@@ -886,8 +869,6 @@ int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, vo
     cudaStream_t s = (cudaStream_t)stream;
     const StageDesc& d = c->staged_block->d;
     int rc;
-    if ((rc = enq_seed_init(c, s, d.pl.RS)) != KA_OK) return set_status(st, rc);
-    if ((rc = enq_tickets(c, s, d)) != KA_OK) return set_status(st, rc);
     if (c->timing) cudaEventRecord(c->ev[3], s);
     if ((rc = enq_order_emit(c, s, d, d_out_broker, d_out_len)) != KA_OK) return set_status(st, rc);
     if (c->timing) cudaEventRecord(c->ev[4], s);
@@ -983,9 +964,9 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     d.Pmax = Pmax;
     d.capmax = capmax;
     c->staged = false;
-    int rc = make_plan(c, Q, S, Pmax, capmax, d.pl, st);
+    int rc = make_plan(c, Q, S, Pmax, capmax, true, d.pl, st);
     if (rc != KA_OK) return rc;
-    if ((rc = reserve_scratch(c, Q, S, T, d.pl.num_chunks)) != KA_OK) return set_status(st, rc);
+    if ((rc = reserve_scratch(c, Q, d.pl.rec_bytes, T, 1, true)) != KA_OK) return set_status(st, rc);
     c->last_stages = 1;
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[0], s));
     if (T > 0) {
@@ -999,11 +980,9 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     c->last_part_id = part_id;
     c->last_part_off = part_off;
     c->ev_mark = c->timing ? c->ev[2] : nullptr;
-    rc = enq_sticky_hist(c, s, d);
+    rc = enq_stage(c, s, d);
     c->ev_mark = nullptr;
     if (rc != KA_OK) return set_status(st, rc);
-    if ((rc = enq_seed_init(c, s, d.pl.RS)) != KA_OK) return set_status(st, rc);
-    if ((rc = enq_tickets(c, s, d)) != KA_OK) return set_status(st, rc);
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
     if ((rc = enq_order_emit(c, s, d, c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>())) != KA_OK) return set_status(st, rc);
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));

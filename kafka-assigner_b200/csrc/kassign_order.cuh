@@ -1,0 +1,415 @@
+// kassign_order.cuh — leader-preference ordering (KAS:202-239, PreferenceListOrderTracker KAS:244-302) against the
+// cross-topic Context.counter (KAS:360-369, KTA:19-23), as a LEVEL-SYNCHRONOUS schedule.
+//
+// Context.counter is shared by every topic of a run (KAG:172), so leader ordering is one serial chain over all partitions
+// of all topics; two partitions commute iff their broker sets are disjoint. Kernel A sorted every topic's partitions into
+// conflict levels (kassign_stage.cuh): the partitions of one level touch pairwise disjoint counter rows. This kernel
+// walks the levels in order with ONE CTA: a level is processed by all threads in parallel (read the three counter rows,
+// take the KAS:226-234 decision, bump counter[list[r]][r]), levels are separated by one named barrier (or __syncwarp when
+// there is a single consumer warp). No tickets, no polling: cost per level = LDS + decision + STS + barrier.
+// The partition records arrive through a TMA ring (cp.async.bulk into shared memory, full/empty mbarriers per stage) fed by
+// a dedicated producer warp, so global latency never touches the chain.
+#pragma once
+#include "kassign_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Chunk tables (only when some topic has more than one level; otherwise level L = topic L = records [L*P, (L+1)*P)).
+// A chunk = at most W consecutive records of ONE level (W = consumer threads of the order kernel).
+//   ntl[t]  chunks of topic t            -> loff[t] = exclusive scan (loff[T] = number of chunks of the block)
+//   lend[g0 + i] topic-relative ends     -> chunk_end[loff[t] + i] = g0 + lend[g0 + i]   (block-relative record positions)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ka_level_scan_kernel(const int32_t* __restrict__ ntl, int T, int32_t* __restrict__ loff) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        const int v = t < T ? ntl[t] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(KA_FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(KA_FULL, w, o);
+                if (lane >= o) w += y;
+            }
+            wsum[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int base = carry + (warp > 0 ? wsum[warp - 1] : 0);
+        if (t < T) loff[t] = base + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = base + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loff[T] = carry;
+}
+
+__global__ void __launch_bounds__(256) ka_level_fill_kernel(const int32_t* __restrict__ ntl, const int32_t* __restrict__ loff,
+                                                            const uint32_t* __restrict__ lend, const int64_t* __restrict__ part_off, int P,
+                                                            int T, uint32_t* __restrict__ lvl_end) {
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= T) return;
+    const int64_t g0 = part_off ? part_off[t] : (int64_t)t * P;
+    const int d = ntl[t], o = loff[t];
+    for (int l = lane; l < d; l += 32) lvl_end[o + l] = (uint32_t)g0 + lend[g0 + l];
+}
+
+// ------------------------------------------------------------------------------------------------
+struct KaOrderParams {
+    uint32_t Q;                 // records (partitions) of the block
+    int N;
+    int S;                      // output row stride (generic kinds write rows themselves)
+    const void* rec;            // schedule-order records (16 B for rows <= 3, else 32 B), 16B aligned. Rows <= 3: each
+                                // record is overwritten in place by the ordered list {o0, o1, o2, f} (o_r = index << 4)
+    uint32_t uniform_width;     // > 0: level L = records [L*w, (L+1)*w), cut into chunks of blockDim-32;  0: chunk table
+    const uint32_t* chunk_end;  // [nchunk] block-relative end position of each chunk (a chunk never spans two levels)
+    const int32_t* nchunk_ptr;  // device scalar: number of chunks (table mode)
+    int32_t* ctr8;              // [N][8] Context.counter for the current broker table (in/out)
+    const int32_t* broker_id;   // RS > 3: rows are written by this kernel
+    int32_t* out;
+    int32_t* out_len;
+    int ring_log2;              // log2(records per ring stage)
+};
+
+#define KA_RING_STAGES 8
+
+__device__ __forceinline__ void ka_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ka_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ka_named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// counter-row access: shared memory (byte address = base + idx*16 .. the record's precomputed offset) or global memory
+// (ctr8 rows of 8 ints, L2-resident; for broker tables beyond shared memory)
+template <bool GCTR> struct KaCtr;
+template <> struct KaCtr<false> {
+    typedef uint32_t H;
+    // a = idx << 4 (record field); CW ints per row in shared memory
+    template <int CW> static __device__ __forceinline__ H row(uint32_t sbase, int32_t*, uint32_t a) { return sbase + (CW == 4 ? a : a * 2u); }
+    static __device__ __forceinline__ int4 ld4(H h, int off) {
+        int4 v;
+        asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(h + off));
+        return v;
+    }
+    static __device__ __forceinline__ void st(H h, int off, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(h + off), "r"(v) : "memory"); }
+};
+template <> struct KaCtr<true> {
+    typedef char* H;
+    template <int CW> static __device__ __forceinline__ H row(uint32_t, int32_t* g, uint32_t a) { return reinterpret_cast<char*>(g) + (size_t)a * 2u; }
+    static __device__ __forceinline__ int4 ld4(H h, int off) {
+        int4 v;
+        asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(h + off));
+        return v;
+    }
+    static __device__ __forceinline__ void st(H h, int off, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(h + off), "r"(v) : "memory"); }
+};
+
+// One selection pass of KAS:263-278 for rows of up to RS replicas (array form; rows of <= 3 use the scalar code below).
+template <int RS>
+__device__ __forceinline__ void ka_order_generic(const int (&c)[RS][RS], int len, uint32_t meta, int (&perm)[RS]) {
+    uint32_t remmask = (1u << len) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+        if (r < len) {
+            const int k = len - r;
+            const int s = ka_rot_of<RS>(meta, k);
+            long long best = 0x7FFFFFFFFFFFFFFFLL;
+            int bpos = 0;
+#pragma unroll
+            for (int pos = 0; pos < RS; ++pos) {
+                if ((remmask >> pos) & 1u) {
+                    int j = __popc(remmask & ((1u << pos) - 1u)) + s;  // position in the rotated scan (KAS:267)
+                    if (j >= k) j -= k;
+                    const long long key = (long long)c[pos][r] * 8 + j;  // strict <, ties to the earlier scan position
+                    if (key < best) { best = key; bpos = pos; }
+                }
+            }
+            perm[r] = bpos;
+            remmask &= ~(1u << bpos);
+        }
+    }
+}
+
+// RS: 3 = rows of <= 3 replicas (16-byte records, pcode out), 4 = rows of 4, 8 = rows of 5..8 (32-byte records, rows
+// written directly). blockDim = NT consumer threads + one producer warp.
+//   producer warp   streams the records into a ring of KA_RING_STAGES shared-memory stages with cp.async.bulk (TMA);
+//                   full[stage] mbarriers carry the byte count, empty[stage] mbarriers hand a consumed stage back
+//   consumers       chunk by chunk (<= NT records, never spanning two levels): thread i takes record i of the chunk,
+//                   loads its counter rows, decides, stores the bumps; one named barrier per chunk is the ONLY
+//                   synchronisation on the chain. The next chunk's record is read from the ring before the barrier.
+template <int RS, bool GCTR, int MAXNT, bool SINGLE, bool WARP1>
+__global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const KaOrderParams p) {
+    constexpr int CW = RS <= 4 ? 4 : 8;          // ints per counter row in shared memory
+    constexpr int RB = RS == 3 ? 16 : 32;        // record bytes
+    constexpr int NS = KA_RING_STAGES;
+    typedef KaCtr<GCTR> C;
+    extern __shared__ __align__(128) unsigned char ka_osmem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    unsigned char* ring = ka_osmem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ka_osmem + ((size_t)NS << p.ring_log2) * RB);
+    uint64_t* empty = full + NS;
+    volatile uint32_t* pin = reinterpret_cast<volatile uint32_t*>(empty + NS);   // 16 words
+    int* ctr = reinterpret_cast<int*>(ka_osmem + ((size_t)NS << p.ring_log2) * RB + 256);
+    // Loop invariants take a round trip through shared memory (volatile) so that they live in registers: ptxas otherwise
+    // re-reads kernel parameters from the constant bank inside the chain loop, and every such load stalls a branch.
+    if (tid == 0) {
+        pin[0] = p.Q; pin[1] = blockDim.x - 32; pin[2] = (uint32_t)p.ring_log2; pin[3] = p.uniform_width;
+        pin[4] = (uint32_t)reinterpret_cast<uintptr_t>(p.rec); pin[5] = (uint32_t)(reinterpret_cast<uintptr_t>(p.rec) >> 32);
+        pin[6] = (uint32_t)reinterpret_cast<uintptr_t>(p.ctr8); pin[7] = (uint32_t)(reinterpret_cast<uintptr_t>(p.ctr8) >> 32);
+    }
+    __syncthreads();
+    const uint32_t Q = pin[0], NT = pin[1];
+    const int LG = (int)pin[2];
+    const uint32_t w = pin[3];
+    uint4* const orec = reinterpret_cast<uint4*>((uintptr_t)pin[4] | ((uintptr_t)pin[5] << 32));
+    int32_t* const ctr8 = reinterpret_cast<int32_t*>((uintptr_t)pin[6] | ((uintptr_t)pin[7] << 32));
+    const uint32_t G = 1u << LG;
+
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { ka_mbar_init(&full[i], 1); ka_mbar_init(&empty[i], 1); }
+        ka_fence_mbar_init();
+    }
+    if (!GCTR)
+        for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += blockDim.x) ctr[i] = ctr8[(i / CW) * KA_MAX_SLOTS + (i % CW)];
+    if (RS == 3 && tid < 4) {  // the dummy row (index N) that pads rows shorter than 3: counters that never win a comparison
+        if (GCTR) ctr8[(size_t)p.N * KA_MAX_SLOTS + tid] = 0x3FFFFFFF; else ctr[p.N * CW + tid] = 0x3FFFFFFF;
+    }
+    // idle lanes read (and ignore) ring slots past the end of the stream: make those valid records (all zero)
+    for (uint32_t i = tid; i < (uint32_t)NS * G * (RB / 16); i += blockDim.x) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+    ka_fence_proxy_async();   // generic-proxy writes above vs the async-proxy (TMA) writes that follow
+    __syncthreads();
+
+    if (tid >= NT) {
+        // ---- producer warp: one elected lane keeps the ring full -------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t nstages = (Q + G - 1) >> LG;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.rec);
+            for (uint32_t j = 0; j < nstages; ++j) {
+                const uint32_t slot = j & (NS - 1);
+                if (j >= (uint32_t)NS) ka_mbar_wait(&empty[slot], ((j / NS) - 1u) & 1u);  // consumers are done with stage j - NS
+                const uint32_t bytes = min(G, Q - (j << LG)) * RB;
+                ka_mbar_expect_tx(&full[slot], bytes);
+                ka_tma_bulk_g2s(ring + (size_t)slot * G * RB, src + (size_t)j * G * RB, bytes, &full[slot]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ------------------------------------------------------------------------------------------------------
+    const uint32_t rmask = (uint32_t)NS * G - 1u;
+    const uint32_t ring_s = ka_smem_u32(ring);
+    uint32_t landed = 0;    // stages this thread has seen complete
+    uint32_t released = 0;  // thread 0: stages handed back to the producer
+    // chunk boundaries
+    const int nchunk = w ? 0 : *p.nchunk_ptr;
+    int wbase = 0;
+    uint32_t wcur = Q, wnxt = Q;  // table mode: chunk_end[wbase + lane], chunk_end[wbase + 32 + lane]
+    if (!w) {
+        wcur = (int)lane < nchunk ? p.chunk_end[lane] : Q;
+        wnxt = 32 + (int)lane < nchunk ? p.chunk_end[32 + lane] : Q;
+    }
+    uint32_t lvl_hi = w;  // uniform mode: end of the level the current chunk belongs to
+    int c = 0;            // chunk ordinal (table mode)
+    auto next_end = [&](uint32_t cur_end) -> uint32_t {  // end of the chunk that starts at cur_end (warp-uniform)
+        if (w) {
+            if (cur_end == lvl_hi) lvl_hi += w;
+            return min(min(cur_end + NT, lvl_hi), Q);
+        }
+        ++c;
+        if (c >= nchunk) return Q;
+        if (c >= wbase + 32) {
+            wcur = wnxt;
+            wbase += 32;
+            const int i = wbase + 32 + (int)lane;
+            wnxt = i < nchunk ? p.chunk_end[i] : Q;
+        }
+        return __shfl_sync(KA_FULL, wcur, c - wbase);
+    };
+    auto read_rec = [&](uint32_t pos, uint4& a, uint4& b) {
+        const uint32_t src = ring_s + (pos & rmask) * RB;
+        asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(src));
+        if (RS != 3) asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(src + 16));
+    };
+    auto cross = [&](uint32_t held_end, uint32_t xlast) {
+        // entering a new ring stage: hand finished stages back FIRST (every record below held_end is already in registers or
+        // done), then wait for the stage(s) the next chunk needs
+        if (tid == 0)
+            while (((released + 1u) << LG) <= held_end) { ka_mbar_arrive(&empty[released & (NS - 1)]); ++released; }
+        const uint32_t j = xlast >> LG;
+        while (landed <= j) { ka_mbar_wait(&full[landed & (NS - 1)], (landed / NS) & 1u); ++landed; }
+    };
+
+    const uint32_t cbase = GCTR ? 0u : ka_smem_u32(ctr);
+    uint32_t start = 0, end = w ? min(min(NT, w), Q) : (nchunk > 0 ? __shfl_sync(KA_FULL, wcur, 0) : Q);
+    uint32_t limit = 0;   // first record position whose ring stage this thread has not seen land yet
+    auto cross_to = [&](uint32_t held_end, uint32_t nend) {
+        cross(held_end, nend - 1u);
+        limit = landed << LG;
+    };
+    uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+    cross_to(0, end);
+    read_rec(start + tid, ra0, ra1);
+
+    if (RS == 3) {
+        // ---- rows of <= 3 replicas: record = {a0, a1, a2, f}: a_j = (index of the broker at position j of the rotated scan of
+        //      KAS:267) << 4; rows shorter than 3 are padded with the DUMMY row (index N, every counter "infinite", so it is
+        //      always ordered last and the code below needs no length dispatch); f = len[0:2) | e01[2] | e02[3] | e12[4], e_pq
+        //      = tie-break of the slot-1 scan over the remaining pair (p, q). One straight-line body per chunk, two branches:
+        //      the ring-stage hand-over (not taken) and the loop. Idle lanes compute on a stale record and store nothing. ----
+#define KA_ORDER3_BODY(RC, RN)                                                                                              \
+        {                                                                                                                       \
+            const uint32_t pos = start + tid;                                                                                   \
+            const bool active = pos < end;                                                                                      \
+            const uint32_t a0 = RC.x, a1 = RC.y, a2 = RC.z, f = RC.w;                                                           \
+            const int4 r0 = C::ld4(C::template row<CW>(cbase, ctr8, a0), 0);                                                    \
+            const int4 r1 = C::ld4(C::template row<CW>(cbase, ctr8, a1), 0);                                                    \
+            const int4 r2 = C::ld4(C::template row<CW>(cbase, ctr8, a2), 0);                                                    \
+            /* next chunk: bounds, stage hand-over, record prefetch: independent of the loads in flight */                    \
+            const uint32_t nstart = end;                                                                                        \
+            const uint32_t nend = SINGLE ? min(end + w, Q) : next_end(end);                                                     \
+            if (__builtin_expect(nend > limit, 0)) cross_to(end, nend);   /* rare: a new ring stage */                          \
+            read_rec(nstart + tid, RN, rb1);                                                                                    \
+            /* slot 0 (KAS:226-234 via getLeastSeenNodeForReplicaId KAS:263-278): strict minimum of counter[.][0] in scan    \
+               order, ties to the earlier scan position: the record is in scan order, so plain '<' decides */                  \
+            const bool L10 = r1.x < r0.x, L20 = r2.x < r0.x, L21 = r2.x < r1.x;                                                 \
+            const bool is2 = L10 ? L21 : L20;                                                                                   \
+            const bool is1 = L10 && !L21;                                                                                       \
+            const bool is0 = !(is1 || is2);                                                                                     \
+            const uint32_t oA = is2 ? a2 : (is1 ? a1 : a0);                                                                     \
+            const int vA = is2 ? r2.x : (is1 ? r1.x : r0.x);                                                                    \
+            /* slot 1: remaining pair (p, q), p < q; q wins iff c_q < c_p + e_pq (e folds id order and |hash| % 2) */          \
+            const uint32_t op = is0 ? a1 : a0, oq = is2 ? a1 : a2;                                                              \
+            const int yp = is0 ? r1.y : r0.y, yq = is2 ? r1.y : r2.y;                                                           \
+            const int zp = is0 ? r1.z : r0.z, zq = is2 ? r1.z : r2.z;                                                           \
+            const bool E01 = (f & 4u) != 0u, E02 = (f & 8u) != 0u, E12 = (f & 16u) != 0u;                                        \
+            const bool e = is2 ? E01 : (is1 ? E02 : E12);                                                                       \
+            const bool pickq = e ? (yq <= yp) : (yq < yp);                                                                      \
+            const uint32_t o1 = pickq ? oq : op, o2 = pickq ? op : oq;                                                          \
+            if (active) {                                                                                                       \
+                C::st(C::template row<CW>(cbase, ctr8, oA), 0, vA + 1);   /* counter[list[r]][r] += 1 (KAS:254-261) */           \
+                C::st(C::template row<CW>(cbase, ctr8, o1), 4, (pickq ? yq : yp) + 1);                                          \
+                C::st(C::template row<CW>(cbase, ctr8, o2), 8, (pickq ? zp : zq) + 1);                                          \
+                /* the ordered list replaces the record (ka_emit3_kernel reads it) */                                           \
+                asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + pos), "r"(oA), "r"(o1), "r"(o2), "r"(f) : "memory"); \
+            }                                                                                                                   \
+            /* level barrier: every counter bump of this chunk is visible before the next chunk reads */                       \
+            if (WARP1) __syncwarp(); else ka_named_bar_sync(1, NT);                                                             \
+            start = nstart; end = nend;                                                                                         \
+        }
+        while (true) {
+            KA_ORDER3_BODY(ra0, rb0)
+            if (start >= Q) break;
+            KA_ORDER3_BODY(rb0, ra0)
+            if (start >= Q) break;
+        }
+#undef KA_ORDER3_BODY
+    } else {
+        while (start < Q) {
+            const uint32_t pos = start + tid;
+            const bool active = pos < end;
+            uint4 nb0, nb1;
+            (void)pos;
+            // ---- rows of 4 / 5..8 replicas: array form, rows written here ---------------------------------------------
+            const uint32_t meta = active ? ra1.x : 0u;
+            const uint32_t orow = ra1.y;
+            const int len = (int)(meta & 15u);
+            uint32_t av[RS];  // broker index << 4
+            av[0] = (ra0.x & 0xFFFFu) << 4; av[1] = (ra0.x >> 16) << 4; av[2] = (ra0.y & 0xFFFFu) << 4; av[3] = (ra0.y >> 16) << 4;
+            if (RS == 8) {
+                av[4] = (ra0.z & 0xFFFFu) << 4; av[5] = (ra0.z >> 16) << 4; av[6] = (ra0.w & 0xFFFFu) << 4; av[7] = (ra0.w >> 16) << 4;
+            }
+            int cv[RS][RS];
+#pragma unroll
+            for (int i = 0; i < RS; ++i) {
+                if (i < len) {
+                    const typename C::H h = C::template row<CW>(cbase, ctr8, av[i]);
+#pragma unroll
+                    for (int v = 0; v < RS; v += 4) {
+                        const int4 rw = C::ld4(h, v * 4);
+                        cv[i][v] = rw.x; cv[i][v + 1] = rw.y; cv[i][v + 2] = rw.z; cv[i][v + 3] = rw.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < RS; ++v) cv[i][v] = 0;
+                }
+            }
+            const uint32_t nstart = end;
+            const uint32_t nend = next_end(end);
+            if (nend > limit) cross_to(end, nend);
+            read_rec(nstart + tid, nb0, nb1);
+            int perm[RS];
+#pragma unroll
+            for (int i = 0; i < RS; ++i) perm[i] = i;
+            if (len > 0) ka_order_generic<RS>(cv, len, meta, perm);
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+                if (r < len) {
+                    uint32_t ba = 0;
+                    int cc = 0;
+#pragma unroll
+                    for (int q = 0; q < RS; ++q)
+                        if (perm[r] == q) { ba = av[q]; cc = cv[q][r]; }
+                    C::st(C::template row<CW>(cbase, ctr8, ba), r * 4, cc + 1);  // counter[list[r]][r] += 1 (KAS:254-261)
+                    if (r < p.S) p.out[(size_t)orow * p.S + r] = __ldg(&p.broker_id[ba >> 4]);
+                } else if (active && r < p.S) {
+                    p.out[(size_t)orow * p.S + r] = -1;
+                }
+            }
+            if (active && p.out_len) p.out_len[orow] = len;
+            if (NT == 32) __syncwarp(); else ka_named_bar_sync(1, NT);
+            start = nstart; end = nend;
+            ra0 = nb0; ra1 = nb1;
+        }
+    }
+
+    if (!GCTR) {
+        if (NT == 32) __syncwarp(); else ka_named_bar_sync(1, NT);
+        for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += NT) ctr8[(i / CW) * KA_MAX_SLOTS + (i % CW)] = ctr[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Emit (rows of <= 3 replicas): ordered record -> broker ids + list length, one thread per schedule
+// position, fully parallel; keeps the id lookups and the 4 B/replica output stream off the serial chain.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ka_emit3_kernel(const uint4* __restrict__ rec, const uint16_t* __restrict__ perm,
+                                                       const int64_t* __restrict__ part_off, int T, int P,
+                                                       const int32_t* __restrict__ broker_id, uint32_t Q, int S, int32_t* __restrict__ out,
+                                                       int32_t* __restrict__ out_len) {
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= Q) return;
+    const uint4 r = rec[pos];   // ordered by the leader-order kernel: {o0, o1, o2, f}
+    const int len = (int)(r.w & 3u);
+    uint32_t row = pos;
+    if (perm) {  // schedule position -> partition row: topic base + ordinal
+        int64_t g0;
+        if (part_off) {
+            int lo = 0, hi = T;  // last topic with part_off[t] <= pos
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (part_off[mid] <= (int64_t)pos) lo = mid; else hi = mid;
+            }
+            g0 = part_off[lo];
+        } else {
+            g0 = (int64_t)(pos / (uint32_t)P) * P;
+        }
+        row = (uint32_t)g0 + perm[pos];
+    }
+    int32_t* o = out + (size_t)row * S;
+    o[0] = len > 0 ? __ldg(broker_id + (r.x >> 4)) : -1;
+    if (S > 1) o[1] = len > 1 ? __ldg(broker_id + (r.y >> 4)) : -1;
+    if (S > 2) o[2] = len > 2 ? __ldg(broker_id + (r.z >> 4)) : -1;
+    if (out_len) out_len[row] = len;
+}

@@ -127,6 +127,10 @@ int32_t ka_solve_dense_device(ka_ctx* ctx, int32_t T, const int32_t* d_topic_has
 int32_t ka_stage_dense_device(ka_ctx* ctx, int32_t T, const int32_t* d_topic_hash, int32_t P, int32_t RF,
                               const int32_t* d_cur_broker, int32_t desired_rf, int32_t out_stride, void* stream);
 int32_t ka_order_device(ka_ctx* ctx, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st);
+/* Index of the staged block's first topic in the whole run: ka_status.topic_index of stage/order solves is reported
+ * relative to the run (rank g of a topic-sharded job passes the number of topics owned by ranks < g), so that the ranks
+ * can agree on the LOWEST failing topic of the run (KAG:173 aborts at the first throw). Default 0. */
+int32_t ka_ctx_set_topic_base(ka_ctx* ctx, int32_t topic_base);
 
 /* Synchronise the last asynchronous solve and return its status. */
 int32_t ka_last_status(ka_ctx* ctx, ka_status* st);
@@ -138,14 +142,16 @@ int32_t ka_last_status(ka_ctx* ctx, ka_status* st);
 int32_t ka_ctx_counter_slots(ka_ctx* ctx);
 int32_t ka_ctx_get_counters(ka_ctx* ctx, int32_t* counter /* [N*slots] host */);
 int32_t ka_ctx_set_counters(ka_ctx* ctx, const int32_t* counter /* [N*slots] host */);
-/* device-to-device variants for NCCL plumbing: d_counter is a device buffer of N*slots int32 */
+/* device-to-device variants for NCCL plumbing: d_counter is a device buffer of N*slots int32. Stream contract: the copy
+ * is enqueued on `stream`; pass the SAME stream as the stage/order calls (or order the streams yourself) — an import
+ * must precede, and an export must follow, the ka_order_device it belongs to in stream order. */
 int32_t ka_ctx_export_counters_device(ka_ctx* ctx, int32_t* d_counter, void* stream);
 int32_t ka_ctx_import_counters_device(ka_ctx* ctx, const int32_t* d_counter, void* stream);
 
 /* ---- instrumentation ----------------------------------------------------------------------------
  * Per-phase device times of the LAST solve, measured with CUDA events on the solve's stream.
- * ms[0]=sticky+spread kernel (S0-S4)  ms[1]=ticket kernels (histogram, scan, rank)
- * ms[2]=leader-order kernel (S5)      ms[3]=H2D   ms[4]=D2H   ms[5]=total on stream
+ * ms[0]=sticky+spread kernel (S0-S4)  ms[1]=chunk tables of the level schedule (scan + fill; 0 when capacity is 1)
+ * ms[2]=leader-order kernel (S5) + emit   ms[3]=H2D   ms[4]=D2H   ms[5]=total on stream
  * Enabled with ka_ctx_set_timing(ctx, 1); costs a few event records per solve. */
 int32_t ka_ctx_set_timing(ka_ctx* ctx, int32_t enabled);
 int32_t ka_ctx_last_timing(ka_ctx* ctx, float* ms /* [8] */);

@@ -131,8 +131,14 @@ class Solver:
     def last_timing(self):
         ms = np.zeros(8, dtype=np.float32)
         self._L.ka_ctx_last_timing(self._h, _ptr(ms))
-        return dict(sticky_spread_ms=float(ms[0]), tickets_ms=float(ms[1]), leader_order_ms=float(ms[2]),
+        return dict(sticky_spread_ms=float(ms[0]), level_tables_ms=float(ms[1]), leader_order_ms=float(ms[2]),
                     h2d_ms=float(ms[3]), d2h_ms=float(ms[4]), total_ms=float(ms[5]))
+
+    def set_topic_base(self, topic_base):
+        """Topic-sharded runs: index of this rank's first topic in the whole run (status reporting)."""
+        rc = self._L.ka_ctx_set_topic_base(self._h, int(topic_base))
+        if rc:
+            raise KassignError(rc)
 
     def launch_count(self):
         return int(self._L.ka_ctx_launch_count(self._h))

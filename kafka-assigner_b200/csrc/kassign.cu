@@ -83,6 +83,8 @@ struct ka_ctx {
     bool ev_valid = false;
     cudaEvent_t ev_mark = nullptr;  // where enq_sticky_hist records 'kernel A done' (timing only)
     int64_t launches = 0;
+    int topic_base = 0;       // ka_ctx_set_topic_base: index of the staged block's first topic in the whole (multi-GPU) run
+    bool last_was_staged = false;
     int order_threads = 0;  // leader-order CTA size override (0 = heuristic from N); env KA_ORDER_THREADS wins
     // second stream + events for the pipelined (super-chunk) solve
     cudaStream_t aux = nullptr;
@@ -522,7 +524,7 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
         const int t = c->h_pin->err_topic;
         KA_CUDA(cudaMemcpy(&c->h_pin->tstatus, c->d_tstatus.as<int4>() + t, sizeof(int4), cudaMemcpyDeviceToHost));
         r.code = c->h_pin->tstatus.x;
-        r.topic_index = t;
+        r.topic_index = t + (c->last_was_staged ? c->topic_base : 0);
         int ord = c->h_pin->tstatus.y;
         r.partition = ord;
         if (ord >= 0 && c->last_part_id && c->last_part_off) r.partition = c->last_part_id[c->last_part_off[t] + ord];
@@ -647,6 +649,7 @@ void ka_ctx_destroy(ka_ctx* c) {
 int32_t ka_ctx_reset(ka_ctx* c) {
     if (!c) return KA_ERR_NO_DEVICE;
     KA_CUDA(cudaSetDevice(c->device));
+    if (c->pending_status) finish_status(c, c->last_stream, nullptr);  // do not race an in-flight asynchronous solve
     c->parked.clear();
     if (c->N > 0 && c->d_ctr8.p) KA_CUDA(cudaMemset(c->d_ctr8.p, 0, (size_t)c->N * KA_MAX_SLOTS * 4));
     return KA_OK;
@@ -814,6 +817,7 @@ int32_t ka_solve_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     c->last_part_id = nullptr;
     c->last_part_off = nullptr;
     c->staged = false;
+    c->last_was_staged = false;
     rc = run_dense(c, s, T, P, RF, desired_rf, out_stride, nullptr, nullptr, const_cast<int32_t*>(d_topic_hash),
                    const_cast<int32_t*>(d_cur_broker), d_out_broker, d_out_len, nullptr, nullptr, st);
     if (rc != KA_OK) { if (st && st->code != rc) set_status(st, rc); return rc; }
@@ -875,9 +879,17 @@ int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, vo
     if ((rc = enq_flags_readback(c, s)) != KA_OK) return set_status(st, rc);
     if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
     c->staged = false;
+    c->last_was_staged = true;
     c->last_stream = s;
     c->pending_status = true;
     if (st) return finish_status(c, s, st);
+    return KA_OK;
+}
+
+int32_t ka_ctx_set_topic_base(ka_ctx* c, int32_t topic_base) {
+    if (!c) return KA_ERR_NO_DEVICE;
+    if (topic_base < 0) return KA_ERR_BAD_ARG;
+    c->topic_base = topic_base;
     return KA_OK;
 }
 
@@ -898,6 +910,7 @@ int32_t ka_solve_dense(ka_ctx* c, int32_t T, const int32_t* topic_hash, int32_t 
     c->last_part_id = nullptr;
     c->last_part_off = nullptr;
     c->staged = false;
+    c->last_was_staged = false;
     rc = run_dense(c, s, T, P, RF, desired_rf, out_stride, topic_hash, cur_broker, c->d_hash.as<int32_t>(), c->d_cur.as<int32_t>(),
                    c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>(), out_broker, out_len, st);
     if (rc != KA_OK) { if (st && st->code != rc) set_status(st, rc); return rc; }
@@ -979,6 +992,7 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[1], s));
     c->last_part_id = part_id;
     c->last_part_off = part_off;
+    c->last_was_staged = false;
     c->ev_mark = c->timing ? c->ev[2] : nullptr;
     rc = enq_stage(c, s, d);
     c->ev_mark = nullptr;

@@ -22,7 +22,27 @@ def shard_range(total_topics, world, rank):
     return t0, t0 + base + (1 if rank < extra else 0)
 
 
-def ring_solve(rank, world, stage, order, export_counters, import_counters, ctr_buf, dist, final_broadcast=True):
+class RunAborted(RuntimeError):
+    """A topic of the run failed on some rank: the reference aborts the whole run at the first failing topic
+    (KafkaAssignmentGenerator.java:173-186 never prints), so every rank raises, with the lowest failing topic index."""
+
+    def __init__(self, topic_index):
+        super().__init__("run aborted: first failing topic %d" % topic_index)
+        self.topic_index = topic_index
+
+
+NO_FAILURE = 2**31 - 1
+
+
+def agree_on_failure(local_first_bad, dist, tensor_factory):
+    """All-reduce (MIN) the first failing GLOBAL topic index of every rank; NO_FAILURE when a rank saw none."""
+    t = tensor_factory([NO_FAILURE if local_first_bad is None else int(local_first_bad)])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t[0])
+
+
+def ring_solve(rank, world, stage, order, export_counters, import_counters, ctr_buf, dist, final_broadcast=True, status=None,
+               tensor_factory=None):
     """Run one topic-sharded solve.
 
     stage():            context-free stage of this rank's block (enqueue only)
@@ -30,6 +50,10 @@ def ring_solve(rank, world, stage, order, export_counters, import_counters, ctr_
     export_counters(t)/import_counters(t): copy the local Context counters to / from tensor t
     ctr_buf:            a tensor [N*slots] int32 on this rank's device, identical shape on all ranks
     dist:               torch.distributed (or a stand-in with send/recv/broadcast)
+    status():           optional; returns None or the GLOBAL index of this rank's first failing topic (synchronises the
+                        rank). When given, the ranks agree on the lowest failing topic of the run, every rank raises
+                        RunAborted and the final broadcast is skipped (counters are undefined after an error). Callers that
+                        keep the solve asynchronous pass None and call agree_on_failure() themselves after synchronising.
     """
     stage()
     if rank > 0:
@@ -39,6 +63,10 @@ def ring_solve(rank, world, stage, order, export_counters, import_counters, ctr_
     if rank < world - 1:
         export_counters(ctr_buf)
         dist.send(ctr_buf, dst=rank + 1)
+    if status is not None:
+        bad = agree_on_failure(status(), dist, tensor_factory)
+        if bad != NO_FAILURE:
+            raise RunAborted(bad)
     if final_broadcast and world > 1:
         if rank == world - 1:
             export_counters(ctr_buf)

@@ -186,12 +186,44 @@ def test_baseline_config1_and_config2_bit_exact(native_lib, oracle):
             assert np.array_equal(out.reshape(-1, 3), exp_out), (key, kind)
 
 
-def test_baseline_config3_prefix_bit_exact(native_lib, oracle):
-    cl = kab.synth.make_config("c3", "mixed").subset(0, 1500)
-    exp_out, _, est = util.oracle_dense(oracle, cl)
-    out, _, st = kab.Solver(0).solve_cluster(cl, check=False)
-    assert st.code == est.code == 0
-    assert np.array_equal(out.reshape(-1, 3), exp_out)
+def _full_compare(oracle, cl, prefix_topics=200, solver=None):
+    """EVERY output row of `cl` against the flat-array CPU solver (pinned to the structure-faithful oracle on these shapes
+    in tests/test_oracle.py::test_fast_solver_pinned_on_baseline_shapes), plus a topic prefix against kafka_oracle.cpp."""
+    s = solver or kab.Solver(0)
+    out, out_len, st = s.solve_cluster(cl, check=False)
+    exp, exp_len, est = oracle.fast_run_dense(oracle.FastContext(), cl.topic_hash, cl.cur, cl.broker_id, cl.rack_index)
+    assert st.code == est.code == 0, (cl.name, st.code, est.code)
+    assert np.array_equal(out.reshape(-1, cl.RF), exp), cl.name
+    assert np.array_equal(out_len.reshape(-1), exp_len), cl.name
+    n = min(cl.T, prefix_topics)
+    pre, _, pst = util.oracle_dense(oracle, cl.subset(0, n))
+    assert pst.code == 0 and np.array_equal(out[:n].reshape(-1, cl.RF), pre), cl.name
+    return s, out, out_len
+
+
+@pytest.mark.parametrize("kind", ["structured", "random", "mixed"])
+def test_baseline_config3_full_bit_exact(native_lib, oracle, kind):
+    """BASELINE config 3 (10k topics x 128, 1k brokers / 20 racks) in full: all 1.28 M rows."""
+    _full_compare(oracle, kab.synth.make_config("c3", kind))
+
+
+def test_baseline_config4_shard_full_bit_exact(native_lib, oracle):
+    """One GPU's eighth of BASELINE config 4 (12.5k topics x 256, 5k brokers / 50 racks) in full."""
+    _full_compare(oracle, kab.synth.make_config("c4shard", "mixed"))
+
+
+def test_baseline_config4_full_bit_exact_on_one_gpu(native_lib, oracle):
+    """BASELINE config 4 itself (100k topics x 256 = 76.8 M assignments, 25.6 M rows) through one Context on one GPU."""
+    cl = kab.synth.make_config("c4", "mixed")
+    _full_compare(oracle, cl, prefix_topics=100)
+
+
+@pytest.mark.parametrize("frac", [0.01, 0.2, 0.5])
+def test_baseline_config5_full_bit_exact(native_lib, oracle, frac):
+    """BASELINE config 5 (decommission sweep: 1 M partitions on 10k brokers / 50 racks, a fraction of every rack removed)."""
+    cl = kab.synth.make_config("c5", "mixed", remove_frac=frac)
+    s, out, _ = _full_compare(oracle, cl, prefix_topics=12)
+    assert not np.isin(out, np.setdiff1d(1000 + np.arange(10000), cl.broker_id)).any()
 
 
 def _check_properties(cl, out, out_len):
@@ -278,17 +310,6 @@ def test_stage_order_split_and_counter_ring_on_one_gpu(native_lib, oracle):
         torch.cuda.synchronize()
         outs.append(do.cpu().numpy().reshape(-1, 3))
     assert np.array_equal(np.concatenate(outs), exp)
-
-
-@pytest.mark.parametrize("frac", [0.01, 0.2, 0.5])
-def test_baseline_config5_decommission_prefix(native_lib, oracle, frac):
-    """BASELINE config 5 shape (10k brokers / 50 racks, 1000-partition topics), a topic prefix, brokers removed."""
-    cl = kab.synth.make_config("c5", "mixed", remove_frac=frac, T=24)
-    exp_out, _, est = util.oracle_dense(oracle, cl)
-    out, _, st = kab.Solver(0).solve_cluster(cl, check=False)
-    assert st.code == est.code == 0
-    assert np.array_equal(out.reshape(-1, 3), exp_out)
-    assert not np.isin(out, np.setdiff1d(1000 + np.arange(10000), cl.broker_id)).any()
 
 
 # ---- less-travelled code paths ----------------------------------------------------------------------------------------

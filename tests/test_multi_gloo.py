@@ -41,8 +41,15 @@ def stage():            # context-free stage: nothing to precompute for the orac
 
 def order():
     po, pid, ro, cur = mine.ragged()
-    ln, _, out, st = ol.run(ctx, mine.topic_names, po, pid, ro, cur, mine.broker_id, mine.rack_name, -1, 3)
-    state["out"] = out
+    desired = int(os.environ.get("KA_TEST_DESIRED_RF", "-1"))
+    if rank != int(os.environ.get("KA_TEST_FAIL_RANK", "-9")):
+        desired = -1
+    try:
+        ln, _, out, st = ol.run(ctx, mine.topic_names, po, pid, ro, cur, mine.broker_id, mine.rack_name, desired, max(3, desired))
+        state["out"] = out
+    except ol.OracleError as e:   # the stand-in backend reports block-local topic indices, like a C-ABI without topic_base
+        state["bad"] = t0 + e.topic_index
+        state["out"] = np.zeros((0, 3), dtype=np.int32)
 
 def export_counters(t):
     for i, b in enumerate(mine.broker_id):
@@ -63,7 +70,13 @@ def import_counters(t):
                 L.oracle_ctx_set_counter(ctx._h, int(b), s, v)
 
 buf = torch.zeros(20 * slots, dtype=torch.int32)
-multi.ring_solve(rank, world, stage, order, export_counters, import_counters, buf, dist)
+try:
+    multi.ring_solve(rank, world, stage, order, export_counters, import_counters, buf, dist, status=lambda: state.get("bad"),
+                     tensor_factory=lambda v: torch.tensor(v, dtype=torch.int64))
+    aborted = -1
+except multi.RunAborted as e:
+    aborted = e.topic_index
+np.save(os.path.join(%(out)r, "abort_%%d.npy" %% rank), np.array([aborted]))
 np.save(os.path.join(%(out)r, "out_%%d.npy" %% rank), state["out"])
 np.save(os.path.join(%(out)r, "ctr_%%d.npy" %% rank), buf.numpy())
 dist.barrier()
@@ -111,3 +124,17 @@ def test_ring_handoff_world2_gloo(tmp_path, oracle):
     for i, b in enumerate(full.broker_id):
         for s in range(3):
             assert c0[i * 8 + s] == octx.counter(int(b), s)
+
+
+def test_failed_topic_aborts_every_rank_with_the_global_index(tmp_path, oracle):
+    """A topic that throws on rank 1 (RF 25 > 20 brokers, KTA:67-69) must abort rank 0 too, with the run-wide topic index,
+    and nobody installs counters from the dead run (ring_solve used to ignore remote failures)."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "out": str(tmp_path)})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", KA_TEST_FAIL_RANK="1", KA_TEST_DESIRED_RF="25")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    t0, _ = multi.shard_range(13, 2, 1)
+    assert int(np.load(tmp_path / "abort_0.npy")[0]) == t0 and int(np.load(tmp_path / "abort_1.npy")[0]) == t0

@@ -164,3 +164,17 @@ def test_fast_cpu_solver_agrees_with_structure_faithful_oracle(oracle):
     exp, _, _ = util.oracle_dense(oracle, c2)
     got, _, st = oracle.fast_run_dense(oracle.FastContext(), c2.topic_hash, c2.cur, c2.broker_id, c2.rack_index)
     assert st.code == 0 and np.array_equal(got, exp)
+
+
+def test_fast_solver_pinned_on_baseline_shapes(oracle):
+    """The flat-array solver is what the -m gpu tests and bench.py compare EVERY row of the big configs against; pin it to the
+    structure-faithful oracle on topic prefixes of exactly those shapes (c3, c4, c5 at three decommission fractions)."""
+    import kafka_assigner_b200 as kab
+    cases = [("c3", dict(T=60), k) for k in ("structured", "random", "mixed")] + [("c4shard", dict(T=16), "mixed")] + \
+            [("c5", dict(T=4, remove_frac=f), "mixed") for f in (0.01, 0.2, 0.5)]
+    for key, over, kind in cases:
+        cl = kab.synth.make_config(key, kind, **over)
+        exp, exp_len, est = util.oracle_dense(oracle, cl)
+        got, got_len, st = oracle.fast_run_dense(oracle.FastContext(), cl.topic_hash, cl.cur, cl.broker_id, cl.rack_index)
+        assert st.code == est.code == 0, (key, kind)
+        assert np.array_equal(got, exp) and np.array_equal(got_len, exp_len), (key, kind)

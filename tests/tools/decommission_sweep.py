@@ -41,6 +41,6 @@ for f in (0.01, 0.02, 0.05, 0.10, 0.20, 0.30, 0.40, 0.50):
     dt = time.perf_counter() - t0
     ok = np.array_equal(d_out.cpu().numpy()[:n].reshape(-1, cl.RF), exp)
     print("| %d%% | %d | %d | %.3f | %.3f | %.3f | %.3f | %.3g | %.3g | %s |" % (
-        round(f * 100), cl.N, -(-cl.P * cl.RF // cl.N), avg["sticky_spread_ms"], avg["tickets_ms"], avg["leader_order_ms"],
+        round(f * 100), cl.N, -(-cl.P * cl.RF // cl.N), avg["sticky_spread_ms"], avg["level_tables_ms"], avg["leader_order_ms"],
         avg["total_ms"], cl.replicas / (avg["total_ms"] * 1e-3), sub.replicas / dt, ok))
     del s

@@ -44,5 +44,5 @@ _, _, exp, _ = ol.run(ol.OracleContext(), sub.topic_names, po, pid, ro, cur, sub
 ok = np.array_equal(d_out.cpu().numpy()[:n].reshape(-1, cl.RF), exp)
 knobs = " ".join("%s=%s" % (k[9:], v) for k, v in sorted(os.environ.items()) if k.startswith("KA_ORDER_"))
 print("%s [%s] KA_ORDER_THREADS=%s A=%.3fms T=%.3fms B=%.3fms total=%.3fms  rate=%.3g/s  verified(first %d topics)=%s" % (
-    a.workload, knobs, os.environ.get("KA_ORDER_THREADS", "-"), avg["sticky_spread_ms"], avg["tickets_ms"], avg["leader_order_ms"],
+    a.workload, knobs, os.environ.get("KA_ORDER_THREADS", "-"), avg["sticky_spread_ms"], avg["level_tables_ms"], avg["leader_order_ms"],
     avg["total_ms"], cl.replicas / (avg["total_ms"] * 1e-3), n, ok))

@@ -132,7 +132,7 @@ class Solver:
         ms = np.zeros(8, dtype=np.float32)
         self._L.ka_ctx_last_timing(self._h, _ptr(ms))
         return dict(sticky_spread_ms=float(ms[0]), level_tables_ms=float(ms[1]), leader_order_ms=float(ms[2]),
-                    h2d_ms=float(ms[3]), d2h_ms=float(ms[4]), total_ms=float(ms[5]))
+                    h2d_ms=float(ms[3]), d2h_ms=float(ms[4]), total_ms=float(ms[5]), slot1_emit_ms=float(ms[6]), chains_wall_ms=float(ms[7]))
 
     def set_topic_base(self, topic_base):
         """Topic-sharded runs: index of this rank's first topic in the whole run (status reporting)."""

@@ -47,6 +47,9 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int KA_MAX_CHAIN_BLOCKS = 8;    // slot-chain sub-blocks per staged block
+constexpr int KA_MAX_CHAIN_EVENTS = 64;   // per solve: 8 staged blocks x 8 sub-blocks
+
 struct HostPinned {
     int err_topic;
     int spin_flag;
@@ -88,6 +91,9 @@ struct ka_ctx {
     int order_threads = 0;  // leader-order CTA size override (0 = heuristic from N); env KA_ORDER_THREADS wins
     // second stream + events for the pipelined (super-chunk) solve
     cudaStream_t aux = nullptr;
+    cudaStream_t sb1 = nullptr;             // slot-0 chain stream (the slot-1 chain + emit run on the caller's stream)
+    cudaEvent_t ev_chain_in = nullptr, ev_b1[KA_MAX_CHAIN_EVENTS] = {}, ev_chain[KA_MAX_CHAIN_EVENTS][4] = {};
+    int chain_ev_next = 0, chain_used = 0;
     cudaEvent_t ev_in = nullptr, ev_stage[8] = {};
     cudaEvent_t ev_pipe[8][5] = {};
     int last_stages = 1;
@@ -177,6 +183,7 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, bool ragged
     // capacity 1 == every broker holds at most one partition of a topic == the topic is a single conflict level
     pl.a_levels = (capmax > 1 || ragged) ? 1 : 0;
     if (const char* e = std::getenv("KA_FORCE_LEVELS")) pl.a_levels = pl.a_levels || std::atoi(e);
+    if (pl.a_levels && Pmax > 32767) return set_status(st, KA_ERR_LIMIT, -1, -1, Pmax, N);  // level cursors are 15-bit
     pl.lv_owner_bytes = pl.a_levels ? (int)align16((size_t)std::max(N, 1) * 4) : 0;
     pl.lv_last_bytes = pl.a_levels ? (int)align16((size_t)std::max(N, 1) * 2) : 0;
     pl.lv_p_bytes = pl.a_levels ? (int)align16((size_t)(std::max(Pmax, 1) + 2) * 2) : 0;
@@ -191,7 +198,8 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, bool ragged
     pl.rec_bytes = pl.rec_kind == 3 ? 16 : 32;
     const int cw = pl.rec_kind == 8 ? 8 : 4;
     const int max_nt = pl.rec_kind == 3 ? 992 : (pl.rec_kind == 4 ? 480 : 224);  // + the producer warp <= 1024 / 512 / 256 threads
-    const size_t ctr_bytes = (size_t)(std::max(N, 1) + 1) * cw * 4;  // + the dummy row that pads rows shorter than 3
+    // rows <= 3: each slot chain keeps ONE counter column (+ the dummy broker that pads short rows) in shared memory
+    const size_t ctr_bytes = pl.rec_kind == 3 ? (size_t)(std::max(N, 1) + 1) * 4 : (size_t)std::max(N, 1) * cw * 4;
     // record ring: KA_RING_STAGES stages of 2^lg records, as large as fits next to the counter table (<= 128 KB)
     const int lg_max = pl.rec_kind == 3 ? 10 : 9, lg_min = 7;
     auto ring_bytes = [&](int l) { return ((size_t)KA_RING_STAGES << l) * pl.rec_bytes + 256; };
@@ -264,6 +272,8 @@ int reserve_scratch(ka_ctx* c, int64_t Qtot, int rec_bytes, int Ttot, int blocks
 int reset_flags(ka_ctx* c, cudaStream_t s) {
     c->h_pin->err_topic = -1;
     c->h_pin->spin_flag = -1;
+    c->chain_ev_next = 0;
+    c->chain_used = 0;
     KA_CUDA(cudaMemsetAsync(c->d_flags.p, 0xFF, 2 * sizeof(int), s));
     return KA_OK;
 }
@@ -349,69 +359,113 @@ int enq_stage(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
     return KA_OK;
 }
 
-template <int RS, int MAXNT, bool GCTR, bool SINGLE, bool WARP1>
+template <int KIND, int MAXNT, bool GCTR, bool SINGLE, bool WARP1>
 cudaError_t launch_order_t(cudaStream_t s, const KaOrderParams& o, const Plan& pl) {
-    auto kern = ka_order_levels_kernel<RS, GCTR, MAXNT, SINGLE, WARP1>;
+    auto kern = ka_order_levels_kernel<KIND, GCTR, MAXNT, SINGLE, WARP1>;
     cudaError_t e = allow_smem(kern, pl.b_smem);
     if (e != cudaSuccess) return e;
     kern<<<1, pl.b_threads + 32, pl.b_smem, s>>>(o);
     return cudaGetLastError();
 }
 
-template <int RS, int MAXNT>
+// KIND 0 / 1: slot chains of rows <= 3 (chunk arithmetic and barrier flavour are compile-time); 4 / 8: rows of 4 / 5..8
+template <int KIND, int MAXNT>
 cudaError_t launch_order(cudaStream_t s, const KaOrderParams& o, const Plan& pl) {
-    if constexpr (RS != 3) {
-        return pl.b_gctr ? launch_order_t<RS, MAXNT, true, false, false>(s, o, pl) : launch_order_t<RS, MAXNT, false, false, false>(s, o, pl);
+    if constexpr (KIND > 1) {
+        return pl.b_gctr ? launch_order_t<KIND, MAXNT, true, false, false>(s, o, pl) : launch_order_t<KIND, MAXNT, false, false, false>(s, o, pl);
     } else {
-    // rows <= 3: chunk arithmetic (one chunk per topic?) and barrier flavour (single consumer warp?) are compile-time
-    const bool single = o.uniform_width != 0 && o.uniform_width <= (uint32_t)pl.b_threads, warp1 = pl.b_threads == 32;
-    const int sel = (pl.b_gctr ? 4 : 0) | (single ? 2 : 0) | (warp1 ? 1 : 0);
-    switch (sel) {
-        case 0: return launch_order_t<3, MAXNT, false, false, false>(s, o, pl);
-        case 1: return launch_order_t<3, MAXNT, false, false, true>(s, o, pl);
-        case 2: return launch_order_t<3, MAXNT, false, true, false>(s, o, pl);
-        case 3: return launch_order_t<3, MAXNT, false, true, true>(s, o, pl);
-        case 4: return launch_order_t<3, MAXNT, true, false, false>(s, o, pl);
-        case 5: return launch_order_t<3, MAXNT, true, false, true>(s, o, pl);
-        case 6: return launch_order_t<3, MAXNT, true, true, false>(s, o, pl);
-        default: return launch_order_t<3, MAXNT, true, true, true>(s, o, pl);
-    }
+        const bool single = o.uniform_width != 0 && o.uniform_width <= (uint32_t)pl.b_threads, warp1 = pl.b_threads == 32;
+        const int sel = (pl.b_gctr ? 4 : 0) | (single ? 2 : 0) | (warp1 ? 1 : 0);
+        switch (sel) {
+            case 0: return launch_order_t<KIND, MAXNT, false, false, false>(s, o, pl);
+            case 1: return launch_order_t<KIND, MAXNT, false, false, true>(s, o, pl);
+            case 2: return launch_order_t<KIND, MAXNT, false, true, false>(s, o, pl);
+            case 3: return launch_order_t<KIND, MAXNT, false, true, true>(s, o, pl);
+            case 4: return launch_order_t<KIND, MAXNT, true, false, false>(s, o, pl);
+            case 5: return launch_order_t<KIND, MAXNT, true, false, true>(s, o, pl);
+            case 6: return launch_order_t<KIND, MAXNT, true, true, false>(s, o, pl);
+            default: return launch_order_t<KIND, MAXNT, true, true, true>(s, o, pl);
+        }
     }
 }
 
-// The serial chain through Context.counter (KAS:202-239) for a block + the parallel emit. d_out/d_out_len: block's rows.
-int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out, int32_t* d_out_len) {
+// How many topic sub-blocks the slot chains of one staged block are cut into: the slot-0 chain of sub-block j+1 runs (on
+// its own SM) while the slot-1 chain + emit of sub-block j run. A chain launch is one CTA, so sub-blocks are cheap; each
+// should still hold a few hundred levels to amortise the launch + ring fill.
+int chain_subblocks(const StageDesc& d, int blocks_in_solve) {
+    if (d.d_part_off || d.pl.rec_kind != 3 || d.T < 2) return 1;
+    int n = std::max(1, 8 / std::max(1, blocks_in_solve));
+    n = std::min(n, std::max(1, d.T / 128));
+    if (const char* e = std::getenv("KA_CHAIN_SUBBLOCKS")) n = std::max(1, std::min(std::atoi(e), d.T));
+    return std::min(n, KA_MAX_CHAIN_BLOCKS);
+}
+
+// The serial chains through Context.counter (KAS:202-239) for a staged block + the parallel emit. d_out/d_out_len: the
+// block's rows. Rows <= 3: slot-0 chain on c->sb1, slot-1 chain + emit on `s`; the caller has made c->sb1 wait for the
+// stage (c->ev_chain_in recorded after kernel A / the counter import). Everything is joined back into `s`.
+int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out, int32_t* d_out_len, int blocks_in_solve) {
     const int N = c->N, S = d.S;
-    const int64_t Q = d.Q;
     const Plan& pl = d.pl;
-    if (Q > 0 && N > 0) {
-        KaOrderParams o{};
-        o.Q = (uint32_t)Q;
-        o.N = N;
-        o.S = S;
-        o.rec = c->d_rec.as<unsigned char>() + (size_t)d.q0 * pl.rec_bytes;
-        o.uniform_width = pl.a_levels ? 0u : (uint32_t)d.P;
-        o.chunk_end = pl.a_levels ? c->d_lvl_end.as<uint32_t>() + d.q0 : nullptr;
-        o.nchunk_ptr = pl.a_levels ? c->d_loff.as<int32_t>() + d.topic_base + d.blk + d.T : nullptr;
-        o.ctr8 = c->d_ctr8.as<int32_t>();
-        o.broker_id = c->d_broker_id.as<int32_t>();
+    if (d.Q <= 0 || N <= 0) return KA_OK;
+    KaOrderParams o{};
+    o.N = N;
+    o.S = S;
+    o.uniform_width = pl.a_levels ? 0u : (uint32_t)d.P;
+    o.chunk_end = pl.a_levels ? c->d_lvl_end.as<uint32_t>() + d.q0 : nullptr;
+    o.ctr8 = c->d_ctr8.as<int32_t>();
+    o.broker_id = c->d_broker_id.as<int32_t>();
+    o.ring_log2 = pl.b_ring_log2;
+    if (const char* e = std::getenv("KA_EXP")) o.exp_flags = std::atoi(e);
+    const int32_t* loff = pl.a_levels ? c->d_loff.as<int32_t>() + d.topic_base + d.blk : nullptr;
+    unsigned char* rec = c->d_rec.as<unsigned char>() + (size_t)d.q0 * pl.rec_bytes;
+    if (pl.rec_kind != 3) {  // rows of 4..8: one fused chain over all slots, rows written by the kernel
+        o.Q = (uint32_t)d.Q;
+        o.rec = rec;
+        o.chunk_lo_ptr = loff;
+        o.chunk_hi_ptr = loff ? loff + d.T : nullptr;
         o.out = d_out;
         o.out_len = d_out_len;
-        o.ring_log2 = pl.b_ring_log2;
-        cudaError_t e;
-        if (pl.rec_kind == 3) e = launch_order<3, 992>(s, o, pl);
-        else if (pl.rec_kind == 4) e = launch_order<4, 480>(s, o, pl);
-        else e = launch_order<8, 224>(s, o, pl);
-        KA_CUDA(e);
+        KA_CUDA((pl.rec_kind == 4 ? launch_order<4, 480>(s, o, pl) : launch_order<8, 224>(s, o, pl)));
         c->launches++;
-        if (pl.rec_kind == 3) {
-            ka_emit3_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(o.rec),
-                                                                        pl.a_levels ? c->d_perm.as<uint16_t>() + d.q0 : nullptr, d.d_part_off, d.T,
-                                                                        d.P, c->d_broker_id.as<int32_t>(), (uint32_t)Q, S, d_out, d_out_len);
-            KA_CUDA(cudaGetLastError());
-            c->launches++;
-        }
+        return KA_OK;
     }
+    const int nsub = chain_subblocks(d, blocks_in_solve);
+    cudaStream_t s1 = c->sb1;
+    for (int j = 0; j < nsub; ++j) {
+        const int t0 = (int)((int64_t)d.T * j / nsub), t1 = (int)((int64_t)d.T * (j + 1) / nsub);
+        // ragged blocks are never cut (nsub == 1): sub-block rows follow from the dense shape
+        const int64_t r0 = d.d_part_off ? 0 : (int64_t)t0 * d.P, rq = d.d_part_off ? d.Q : (int64_t)(t1 - t0) * d.P;
+        if (rq <= 0) continue;
+        o.Q = (uint32_t)rq;
+        o.rec = rec + (size_t)r0 * pl.rec_bytes;
+        o.pos_base = (uint32_t)r0;
+        o.chunk_lo_ptr = loff ? loff + t0 : nullptr;
+        o.chunk_hi_ptr = loff ? loff + t1 : nullptr;
+        const int e = c->chain_ev_next++ % KA_MAX_CHAIN_EVENTS;
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][0], s1));
+        KA_CUDA((launch_order<0, 992>(s1, o, pl)));                      // slot-0 chain
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][1], s1));
+        KA_CUDA(cudaEventRecord(c->ev_b1[e], s1));
+        KA_CUDA(cudaStreamWaitEvent(s, c->ev_b1[e], 0));
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][2], s));
+        KA_CUDA((launch_order<1, 992>(s, o, pl)));                       // slot-1 chain
+        ka_emit3_kernel<<<(unsigned)((rq + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(o.rec),
+                                                                     pl.a_levels ? c->d_perm.as<uint16_t>() + d.q0 + r0 : nullptr, d.d_part_off,
+                                                                     t1 - t0, d.P, c->d_broker_id.as<int32_t>(), (uint32_t)rq, S,
+                                                                     d_out + (size_t)r0 * S, d_out_len ? d_out_len + r0 : nullptr,
+                                                                     c->d_ctr8.as<int32_t>());
+        KA_CUDA(cudaGetLastError());
+        if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][3], s));
+        c->chain_used = std::min(c->chain_used + 1, KA_MAX_CHAIN_EVENTS);
+        c->launches += 3;
+    }
+    return KA_OK;
+}
+
+// c->sb1 (slot-0 chain stream) must see everything enqueued on `s` so far: the staged records / imported counters
+int chain_fork(ka_ctx* c, cudaStream_t s) {
+    KA_CUDA(cudaEventRecord(c->ev_chain_in, s));
+    KA_CUDA(cudaStreamWaitEvent(c->sb1, c->ev_chain_in, 0));
     return KA_OK;
 }
 
@@ -475,7 +529,8 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
         if ((rc = enq_stage(c, s, d)) != KA_OK) return rc;
         c->ev_mark = nullptr;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
-        if ((rc = enq_order_emit(c, s, d, d_out, d_out_len)) != KA_OK) return rc;
+        if ((rc = chain_fork(c, s)) != KA_OK) return rc;
+        if ((rc = enq_order_emit(c, s, d, d_out, d_out_len, 1)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
         if (h_out && Q > 0 && c->N > 0) {
             KA_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)Q * S * 4, cudaMemcpyDeviceToHost, s));
@@ -498,8 +553,10 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][2], aux));
             KA_CUDA(cudaEventRecord(c->ev_stage[k], aux));
             KA_CUDA(cudaStreamWaitEvent(s_main, c->ev_stage[k], 0));
+            KA_CUDA(cudaStreamWaitEvent(c->sb1, c->ev_stage[k], 0));
+            if (k == 0) KA_CUDA(cudaStreamWaitEvent(c->sb1, c->ev_in, 0));
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][3], s_main));
-            if ((rc = enq_order_emit(c, s_main, d, d_out + d.q0 * S, d_out_len ? d_out_len + d.q0 : nullptr)) != KA_OK) return rc;
+            if ((rc = enq_order_emit(c, s_main, d, d_out + d.q0 * S, d_out_len ? d_out_len + d.q0 : nullptr, K)) != KA_OK) return rc;
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][4], s_main));
             if (h_out && d.Q > 0 && c->N > 0) {
                 KA_CUDA(cudaMemcpyAsync(h_out + d.q0 * S, d_out + d.q0 * S, (size_t)d.Q * S * 4, cudaMemcpyDeviceToHost, s_main));
@@ -538,7 +595,7 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
             cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]);  // H2D
             cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]);  // kernel A
             cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);  // level tables (scan + fill; absent when capacity is 1)
-            cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);  // kernel B + emit
+            cudaEventElapsedTime(&c->last_ms[7], c->ev[3], c->ev[4]);  // all chains + emit, wall time on the stream
             cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);  // D2H
         } else {  // pipelined: phases of different chunks overlap; report the per-phase sums
             for (int k = 0; k < c->last_stages; ++k) {
@@ -548,8 +605,19 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
                 cudaEventElapsedTime(&b, c->ev_pipe[k][3], c->ev_pipe[k][4]);
                 c->last_ms[0] += a;
                 c->last_ms[1] += t;
-                c->last_ms[2] += b;
+                c->last_ms[7] += b;
             }
+        }
+        if (c->chain_used > 0) {  // rows <= 3: per-slot chains (sums over the sub-blocks; the two chains overlap in time)
+            for (int e = 0; e < c->chain_used; ++e) {
+                float b1 = 0.f, b2 = 0.f;
+                cudaEventElapsedTime(&b1, c->ev_chain[e][0], c->ev_chain[e][1]);
+                cudaEventElapsedTime(&b2, c->ev_chain[e][2], c->ev_chain[e][3]);
+                c->last_ms[2] += b1;
+                c->last_ms[6] += b2;
+            }
+        } else {
+            c->last_ms[2] = c->last_ms[7];  // rows of 4..8: one fused chain
         }
     }
     c->last = r;
@@ -619,6 +687,11 @@ ka_ctx* ka_ctx_create(int32_t device) {
     if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_pin), sizeof(HostPinned), cudaHostAllocDefault) != cudaSuccess) { delete c; return nullptr; }
     for (auto& e : c->ev) cudaEventCreate(&e);
     if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    if (cudaStreamCreateWithFlags(&c->sb1, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    cudaEventCreateWithFlags(&c->ev_chain_in, cudaEventDisableTiming);
+    for (auto& e : c->ev_b1) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& row : c->ev_chain)
+        for (auto& e : row) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     for (auto& e : c->ev_stage) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& row : c->ev_pipe)
@@ -636,6 +709,11 @@ void ka_ctx_destroy(ka_ctx* c) {
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+    if (c->sb1) { cudaStreamSynchronize(c->sb1); cudaStreamDestroy(c->sb1); }
+    if (c->ev_chain_in) cudaEventDestroy(c->ev_chain_in);
+    for (auto& e : c->ev_b1) if (e) cudaEventDestroy(e);
+    for (auto& row : c->ev_chain)
+        for (auto& e : row) if (e) cudaEventDestroy(e);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     for (auto& e : c->ev_stage) if (e) cudaEventDestroy(e);
     for (auto& row : c->ev_pipe)
@@ -874,7 +952,8 @@ int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, vo
     const StageDesc& d = c->staged_block->d;
     int rc;
     if (c->timing) cudaEventRecord(c->ev[3], s);
-    if ((rc = enq_order_emit(c, s, d, d_out_broker, d_out_len)) != KA_OK) return set_status(st, rc);
+    if ((rc = chain_fork(c, s)) != KA_OK) return set_status(st, rc);
+    if ((rc = enq_order_emit(c, s, d, d_out_broker, d_out_len, 1)) != KA_OK) return set_status(st, rc);
     if (c->timing) cudaEventRecord(c->ev[4], s);
     if ((rc = enq_flags_readback(c, s)) != KA_OK) return set_status(st, rc);
     if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
@@ -998,7 +1077,8 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     c->ev_mark = nullptr;
     if (rc != KA_OK) return set_status(st, rc);
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[3], s));
-    if ((rc = enq_order_emit(c, s, d, c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>())) != KA_OK) return set_status(st, rc);
+    if ((rc = chain_fork(c, s)) != KA_OK) return set_status(st, rc);
+    if ((rc = enq_order_emit(c, s, d, c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>(), 1)) != KA_OK) return set_status(st, rc);
     if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
     if (Q > 0 && c->N > 0) {
         KA_CUDA(cudaMemcpyAsync(out_broker, c->d_out.p, (size_t)Q * S * 4, cudaMemcpyDeviceToHost, s));

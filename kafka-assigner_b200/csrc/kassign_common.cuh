@@ -33,11 +33,12 @@ enum { KA_LUT_SMEM = 0, KA_LUT_GLOBAL = 1, KA_LUT_BSEARCH = 2 };
 // Partition records: what kernel A hands to the leader-order kernel, in SCHEDULE order (topic by topic; inside a
 // topic by conflict level, then partition ascending). Broker indices are positions in the ascending live-id table.
 //   rows of <= 3 replicas  uint4 {a0, a1, a2, f}: a_j = (index of the broker at position j of the slot-0 scan order of
-//                          KAS:267, i.e. ascending list position i sits at j = (i + |hash| % len) % len) << 4 = byte offset
-//                          of that broker's 16 B counter row; unused slots alias slot 0;
-//                          f = len[0:2) | e01[2] | e02[3] | e12[4], e_pq = tie-break of the slot-1 scan over the pair
+//                          KAS:267, i.e. ascending list position i sits at j = (i + |hash| % len) % len) << 2 = byte offset
+//                          of that broker's counter in a 4-byte column; unused slots = the dummy broker N;
+//                          f = len[0:2) | e01[2] | e02[3] | e12[4] | first-of-level[7], e_pq = tie-break of the slot-1 scan over the pair
 //                          (p, q) left when the third position took slot 0 (see kassign_stage.cuh / kassign_order.cuh).
-//                          The order kernel overwrites the record with the ordered list {o0, o1, o2, f}.
+//                          The slot-0 chain rewrites it as {op, oq, len | e << 2, o0} (remaining pair in scan order, its
+//                          tie-break, the slot-0 broker); the slot-1 chain as the ordered list {o0, o1, o2, len | e << 2}.
 //   rows of 4..8           2 x uint4 : {idx0|idx1<<16, idx2|idx3<<16, idx4|idx5<<16, idx6|idx7<<16}, {meta32, row, 0, 0}
 //                          meta32 = len[0:4) | rotations for k = 2..8 (ka_rot_bits), row = block-relative output row
 // ------------------------------------------------------------------------------------------------

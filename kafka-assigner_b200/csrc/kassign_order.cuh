@@ -73,13 +73,16 @@ struct KaOrderParams {
     const void* rec;            // schedule-order records (16 B for rows <= 3, else 32 B), 16B aligned. Rows <= 3: each
                                 // record is overwritten in place by the ordered list {o0, o1, o2, f} (o_r = index << 4)
     uint32_t uniform_width;     // > 0: level L = records [L*w, (L+1)*w), cut into chunks of blockDim-32;  0: chunk table
-    const uint32_t* chunk_end;  // [nchunk] block-relative end position of each chunk (a chunk never spans two levels)
-    const int32_t* nchunk_ptr;  // device scalar: number of chunks (table mode)
+    const uint32_t* chunk_end;  // table mode: end position of each chunk of the STAGED block (a chunk never spans two levels)
+    const int32_t* chunk_lo_ptr;  // device scalars: this launch walks chunks [*chunk_lo_ptr, *chunk_hi_ptr) of that table
+    const int32_t* chunk_hi_ptr;  //   (loff[] of ka_level_scan_kernel at the first / one-past-last topic of the launch)
+    uint32_t pos_base;          // record position of p.rec[0] inside the staged block (chunk_end values are block-relative)
     int32_t* ctr8;              // [N][8] Context.counter for the current broker table (in/out)
     const int32_t* broker_id;   // RS > 3: rows are written by this kernel
     int32_t* out;
     int32_t* out_len;
     int ring_log2;              // log2(records per ring stage)
+    int exp_flags;              // timing experiments only (KA_EXP env): 1 = skip the global record store
 };
 
 #define KA_RING_STAGES 8
@@ -104,6 +107,14 @@ template <> struct KaCtr<false> {
         return v;
     }
     static __device__ __forceinline__ void st(H h, int off, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(h + off), "r"(v) : "memory"); }
+    // slot chains: one counter column in shared memory, a = idx << 2
+    static __device__ __forceinline__ H col(uint32_t sbase, int32_t*, uint32_t a, int) { return sbase + a; }
+    static __device__ __forceinline__ int ld1(H h) {
+        int v;
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(h));
+        return v;
+    }
+    static __device__ __forceinline__ void st1(H h, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(h), "r"(v) : "memory"); }
 };
 template <> struct KaCtr<true> {
     typedef char* H;
@@ -114,6 +125,13 @@ template <> struct KaCtr<true> {
         return v;
     }
     static __device__ __forceinline__ void st(H h, int off, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(h + off), "r"(v) : "memory"); }
+    static __device__ __forceinline__ H col(uint32_t, int32_t* g, uint32_t a, int slot) { return reinterpret_cast<char*>(g) + (size_t)a * 8u + slot * 4; }
+    static __device__ __forceinline__ int ld1(H h) {
+        int v;
+        asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(h));
+        return v;
+    }
+    static __device__ __forceinline__ void st1(H h, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(h), "r"(v) : "memory"); }
 };
 
 // One selection pass of KAS:263-278 for rows of up to RS replicas (array form; rows of <= 3 use the scalar code below).
@@ -142,17 +160,18 @@ __device__ __forceinline__ void ka_order_generic(const int (&c)[RS][RS], int len
     }
 }
 
-// RS: 3 = rows of <= 3 replicas (16-byte records, pcode out), 4 = rows of 4, 8 = rows of 5..8 (32-byte records, rows
-// written directly). blockDim = NT consumer threads + one producer warp.
+// KIND 0 / 1 = slot-0 / slot-1 chain of rows <= 3 (16-byte records, rewritten in place), 4 = rows of 4, 8 = rows of 5..8
+// (32-byte records, all slots in one chain, rows written directly). blockDim = NT consumer threads + one producer warp.
 //   producer warp   streams the records into a ring of KA_RING_STAGES shared-memory stages with cp.async.bulk (TMA);
 //                   full[stage] mbarriers carry the byte count, empty[stage] mbarriers hand a consumed stage back
 //   consumers       chunk by chunk (<= NT records, never spanning two levels): thread i takes record i of the chunk,
 //                   loads its counter rows, decides, stores the bumps; one named barrier per chunk is the ONLY
 //                   synchronisation on the chain. The next chunk's record is read from the ring before the barrier.
-template <int RS, bool GCTR, int MAXNT, bool SINGLE, bool WARP1>
+template <int KIND, bool GCTR, int MAXNT, bool SINGLE, bool WARP1>
 __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const KaOrderParams p) {
-    constexpr int CW = RS <= 4 ? 4 : 8;          // ints per counter row in shared memory
-    constexpr int RB = RS == 3 ? 16 : 32;        // record bytes
+    constexpr int RS = KIND <= 1 ? 3 : KIND;                 // KIND 0 / 1: slot-0 / slot-1 chain of rows <= 3; 4 / 8: rows of 4 / 5..8
+    constexpr int CW = KIND <= 1 ? 1 : (KIND == 4 ? 4 : 8);  // ints per broker in shared memory (one counter column for the slot chains)
+    constexpr int RB = RS == 3 ? 16 : 32;                    // record bytes
     constexpr int NS = KA_RING_STAGES;
     typedef KaCtr<GCTR> C;
     extern __shared__ __align__(128) unsigned char ka_osmem[];
@@ -168,11 +187,13 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
         pin[0] = p.Q; pin[1] = blockDim.x - 32; pin[2] = (uint32_t)p.ring_log2; pin[3] = p.uniform_width;
         pin[4] = (uint32_t)reinterpret_cast<uintptr_t>(p.rec); pin[5] = (uint32_t)(reinterpret_cast<uintptr_t>(p.rec) >> 32);
         pin[6] = (uint32_t)reinterpret_cast<uintptr_t>(p.ctr8); pin[7] = (uint32_t)(reinterpret_cast<uintptr_t>(p.ctr8) >> 32);
+        pin[8] = (uint32_t)p.exp_flags;
     }
     __syncthreads();
     const uint32_t Q = pin[0], NT = pin[1];
     const int LG = (int)pin[2];
     const uint32_t w = pin[3];
+    const uint32_t expf = pin[8];
     uint4* const orec = reinterpret_cast<uint4*>((uintptr_t)pin[4] | ((uintptr_t)pin[5] << 32));
     int32_t* const ctr8 = reinterpret_cast<int32_t*>((uintptr_t)pin[6] | ((uintptr_t)pin[7] << 32));
     const uint32_t G = 1u << LG;
@@ -182,9 +203,10 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
         ka_fence_mbar_init();
     }
     if (!GCTR)
-        for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += blockDim.x) ctr[i] = ctr8[(i / CW) * KA_MAX_SLOTS + (i % CW)];
-    if (RS == 3 && tid < 4) {  // the dummy row (index N) that pads rows shorter than 3: counters that never win a comparison
-        if (GCTR) ctr8[(size_t)p.N * KA_MAX_SLOTS + tid] = 0x3FFFFFFF; else ctr[p.N * CW + tid] = 0x3FFFFFFF;
+        for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += blockDim.x)
+            ctr[i] = ctr8[(i / CW) * KA_MAX_SLOTS + (KIND <= 1 ? KIND : (int)(i % CW))];
+    if (KIND <= 1 && tid == 0) {  // the dummy broker (index N) that pads rows shorter than 3: a counter that never wins a comparison
+        if (GCTR) ctr8[(size_t)p.N * KA_MAX_SLOTS + KIND] = 0x3FFFFFFF; else ctr[p.N] = 0x3FFFFFFF;
     }
     // idle lanes read (and ignore) ring slots past the end of the stream: make those valid records (all zero)
     for (uint32_t i = tid; i < (uint32_t)NS * G * (RB / 16); i += blockDim.x) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
@@ -213,12 +235,15 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
     uint32_t landed = 0;    // stages this thread has seen complete
     uint32_t released = 0;  // thread 0: stages handed back to the producer
     // chunk boundaries
-    const int nchunk = w ? 0 : *p.nchunk_ptr;
+    const int chunk_lo = w ? 0 : *p.chunk_lo_ptr;
+    const int nchunk = w ? 0 : *p.chunk_hi_ptr - chunk_lo;
+    const uint32_t* const cend = p.chunk_end + chunk_lo;
+    const uint32_t pos_base = p.pos_base;
     int wbase = 0;
-    uint32_t wcur = Q, wnxt = Q;  // table mode: chunk_end[wbase + lane], chunk_end[wbase + 32 + lane]
+    uint32_t wcur = Q, wnxt = Q;  // table mode: chunk end of chunk wbase + lane, wbase + 32 + lane
     if (!w) {
-        wcur = (int)lane < nchunk ? p.chunk_end[lane] : Q;
-        wnxt = 32 + (int)lane < nchunk ? p.chunk_end[32 + lane] : Q;
+        wcur = (int)lane < nchunk ? cend[lane] - pos_base : Q;
+        wnxt = 32 + (int)lane < nchunk ? cend[32 + lane] - pos_base : Q;
     }
     uint32_t lvl_hi = w;  // uniform mode: end of the level the current chunk belongs to
     int c = 0;            // chunk ordinal (table mode)
@@ -233,7 +258,7 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
             wcur = wnxt;
             wbase += 32;
             const int i = wbase + 32 + (int)lane;
-            wnxt = i < nchunk ? p.chunk_end[i] : Q;
+            wnxt = i < nchunk ? cend[i] - pos_base : Q;
         }
         return __shfl_sync(KA_FULL, wcur, c - wbase);
     };
@@ -262,59 +287,189 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
     cross_to(0, end);
     read_rec(start + tid, ra0, ra1);
 
-    if (RS == 3) {
-        // ---- rows of <= 3 replicas: record = {a0, a1, a2, f}: a_j = (index of the broker at position j of the rotated scan of
-        //      KAS:267) << 4; rows shorter than 3 are padded with the DUMMY row (index N, every counter "infinite", so it is
-        //      always ordered last and the code below needs no length dispatch); f = len[0:2) | e01[2] | e02[3] | e12[4], e_pq
-        //      = tie-break of the slot-1 scan over the remaining pair (p, q). One straight-line body per chunk, two branches:
-        //      the ring-stage hand-over (not taken) and the loop. Idle lanes compute on a stale record and store nothing. ----
-#define KA_ORDER3_BODY(RC, RN)                                                                                              \
-        {                                                                                                                       \
-            const uint32_t pos = start + tid;                                                                                   \
-            const bool active = pos < end;                                                                                      \
+    // ---- slot chains (rows <= 3) ------------------------------------------------------------------------------------------
+    // slot-0 chain: record = {a0, a1, a2, f}: a_j = (index of the broker at position j of the rotated scan of KAS:267) << 2 =
+    //   byte offset of its counter in a column; rows shorter than 3 are padded with the DUMMY broker (index N, "infinite"
+    //   counter: always ordered last, so no length dispatch); f = len[0:2) | e01[2] | e02[3] | e12[4]. Slot 0 reads and bumps
+    //   ONLY counter[.][0] (getLeastSeenNodeForReplicaId(0, .), KAS:263-278), so this chain does not wait for the slot-1
+    //   decisions: it hands {remaining pair, tie-break, leader} to the slot-1 chain in place of the record.
+    // slot-1 chain: record = {op, oq, f, oA}: the two brokers left after slot 0 in scan order, f = len[0:2) | e[2], the slot-0
+    //   broker. q takes slot 1 iff c_q < c_p + e (e folds the ascending-id order and |hash| % 2 of the second
+    //   getNodeProcessingOrder call, KAS:267); only counter[.][1] is read and bumped. The last broker's counter[.][2] is
+    //   write-only for rows <= 3: ka_emit3_kernel adds it in parallel.
+    // Idle lanes compute on a stale (valid) record and store nothing.
+#define KA_SLOT0_CORE(RC, ACTIVE, POS)                                                                                          \
             const uint32_t a0 = RC.x, a1 = RC.y, a2 = RC.z, f = RC.w;                                                           \
-            const int4 r0 = C::ld4(C::template row<CW>(cbase, ctr8, a0), 0);                                                    \
-            const int4 r1 = C::ld4(C::template row<CW>(cbase, ctr8, a1), 0);                                                    \
-            const int4 r2 = C::ld4(C::template row<CW>(cbase, ctr8, a2), 0);                                                    \
-            /* next chunk: bounds, stage hand-over, record prefetch: independent of the loads in flight */                    \
-            const uint32_t nstart = end;                                                                                        \
-            const uint32_t nend = SINGLE ? min(end + w, Q) : next_end(end);                                                     \
-            if (__builtin_expect(nend > limit, 0)) cross_to(end, nend);   /* rare: a new ring stage */                          \
-            read_rec(nstart + tid, RN, rb1);                                                                                    \
-            /* slot 0 (KAS:226-234 via getLeastSeenNodeForReplicaId KAS:263-278): strict minimum of counter[.][0] in scan    \
-               order, ties to the earlier scan position: the record is in scan order, so plain '<' decides */                  \
-            const bool L10 = r1.x < r0.x, L20 = r2.x < r0.x, L21 = r2.x < r1.x;                                                 \
+            const int x0 = C::ld1(C::col(cbase, ctr8, a0, 0)), x1 = C::ld1(C::col(cbase, ctr8, a1, 0)), x2 = C::ld1(C::col(cbase, ctr8, a2, 0));
+#define KA_SLOT0_DECIDE(ACTIVE, POS)                                                                                            \
+            /* strict minimum in scan order, ties to the earlier scan position: the record IS in scan order */                 \
+            const bool L10 = x1 < x0, L20 = x2 < x0, L21 = x2 < x1;                                                             \
             const bool is2 = L10 ? L21 : L20;                                                                                   \
             const bool is1 = L10 && !L21;                                                                                       \
             const bool is0 = !(is1 || is2);                                                                                     \
             const uint32_t oA = is2 ? a2 : (is1 ? a1 : a0);                                                                     \
-            const int vA = is2 ? r2.x : (is1 ? r1.x : r0.x);                                                                    \
-            /* slot 1: remaining pair (p, q), p < q; q wins iff c_q < c_p + e_pq (e folds id order and |hash| % 2) */          \
+            const int vA = is2 ? x2 : (is1 ? x1 : x0);                                                                          \
+            /* remaining pair (p, q), p < q in scan order, and the tie-break e_pq of its slot-1 scan */                        \
             const uint32_t op = is0 ? a1 : a0, oq = is2 ? a1 : a2;                                                              \
-            const int yp = is0 ? r1.y : r0.y, yq = is2 ? r1.y : r2.y;                                                           \
-            const int zp = is0 ? r1.z : r0.z, zq = is2 ? r1.z : r2.z;                                                           \
-            const bool E01 = (f & 4u) != 0u, E02 = (f & 8u) != 0u, E12 = (f & 16u) != 0u;                                        \
-            const bool e = is2 ? E01 : (is1 ? E02 : E12);                                                                       \
-            const bool pickq = e ? (yq <= yp) : (yq < yp);                                                                      \
+            const uint32_t esh = is2 ? f : (is1 ? f >> 1 : f >> 2);                                                             \
+            if (ACTIVE) {                                                                                                       \
+                if (!(expf & 2)) C::st1(C::col(cbase, ctr8, oA, 0), vA + 1);   /* counter[list[0]][0] += 1 (KAS:254-261) */      \
+                if (!(expf & 1)) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + (POS)), "r"(op), "r"(oq), "r"((f & 0x83u) | (esh & 4u)), "r"(oA) : "memory"); \
+            }
+#define KA_SLOT1_CORE(RC, ACTIVE, POS)                                                                                          \
+            const uint32_t op = RC.x, oq = RC.y, f = RC.z, oA = RC.w;                                                           \
+            const int yp = C::ld1(C::col(cbase, ctr8, op, 1)), yq = C::ld1(C::col(cbase, ctr8, oq, 1));
+#define KA_SLOT1_DECIDE(ACTIVE, POS)                                                                                            \
+            const bool pickq = yq < yp + (int)((f >> 2) & 1u);                                                                  \
             const uint32_t o1 = pickq ? oq : op, o2 = pickq ? op : oq;                                                          \
-            if (active) {                                                                                                       \
-                C::st(C::template row<CW>(cbase, ctr8, oA), 0, vA + 1);   /* counter[list[r]][r] += 1 (KAS:254-261) */           \
-                C::st(C::template row<CW>(cbase, ctr8, o1), 4, (pickq ? yq : yp) + 1);                                          \
-                C::st(C::template row<CW>(cbase, ctr8, o2), 8, (pickq ? zp : zq) + 1);                                          \
+            if (ACTIVE) {                                                                                                       \
+                C::st1(C::col(cbase, ctr8, o1, 1), (pickq ? yq : yp) + 1);   /* counter[list[1]][1] += 1 (KAS:254-261) */        \
                 /* the ordered list replaces the record (ka_emit3_kernel reads it) */                                           \
-                asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + pos), "r"(oA), "r"(o1), "r"(o2), "r"(f) : "memory"); \
+                asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + (POS)), "r"(oA), "r"(o1), "r"(o2), "r"(f) : "memory"); \
+            }
+    if (KIND <= 1 && WARP1) {
+        // ---- single consumer warp (narrow levels): WINDOW mode. 32 consecutive records per iteration; bit 7 of f marks the
+        //      first record of a level, so the window splits into level groups by one ballot — no chunk table. Only the
+        //      counter-critical part (load, compare, bump) runs once per group, separated by __syncwarp; everything that does
+        //      not touch the counters (remaining pair, tie-break, record store) runs once per window at full width. -----------
+        const uint32_t lmle = ka_lanemask_lt() | (1u << lane);
+        for (uint32_t wstart = 0; wstart < Q;) {
+            const uint32_t pos = wstart + tid;
+            const uint32_t f = KIND == 0 ? ra0.w : ra0.z;
+            const uint32_t bal = __ballot_sync(KA_FULL, pos < Q && (f & 0x80u)) | 1u;   // lane 0 continues or opens a group
+            // (cutting windows at level boundaries — whole levels only — was measured: fewer groups but more windows, slower)
+            const int ngrp = __popc(bal);
+            const uint32_t take = 32u;
+            const bool active = pos < Q;
+            const int grp = __popc(bal & lmle) - 1;
+            const uint32_t nstart = wstart + take, need = min(nstart + 32u, Q);
+            if (__builtin_expect(need > limit, 0)) cross_to(nstart, need);   // rare: the next window enters a new ring stage
+            read_rec(nstart + tid, rb0, rb1);
+            if (KIND == 0) {
+                const uint32_t a0 = ra0.x, a1 = ra0.y, a2 = ra0.z;
+                bool is1 = false, is2 = false;
+                for (int g = 0; g < ngrp; ++g) {
+                    if (grp == g && active) {
+                        const int x0 = C::ld1(C::col(cbase, ctr8, a0, 0)), x1 = C::ld1(C::col(cbase, ctr8, a1, 0)), x2 = C::ld1(C::col(cbase, ctr8, a2, 0));
+                        const bool L10 = x1 < x0, L20 = x2 < x0, L21 = x2 < x1;   // scan order: strict '<', ties to the earlier
+                        is2 = L10 ? L21 : L20;
+                        is1 = L10 && !L21;
+                        C::st1(C::col(cbase, ctr8, is2 ? a2 : (is1 ? a1 : a0), 0), (is2 ? x2 : (is1 ? x1 : x0)) + 1);   // KAS:254-261
+                    }
+                    __syncwarp();   // level barrier
+                }
+                const bool is0 = !(is1 || is2);
+                const uint32_t oA = is2 ? a2 : (is1 ? a1 : a0), op = is0 ? a1 : a0, oq = is2 ? a1 : a2;
+                const uint32_t esh = is2 ? f : (is1 ? f >> 1 : f >> 2);
+                if (active) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + pos), "r"(op), "r"(oq), "r"((f & 0x83u) | (esh & 4u)), "r"(oA) : "memory");
+            } else {
+                const uint32_t op = ra0.x, oq = ra0.y, oA = ra0.w;
+                bool pickq = false;
+                for (int g = 0; g < ngrp; ++g) {
+                    if (grp == g && active) {
+                        const int yp = C::ld1(C::col(cbase, ctr8, op, 1)), yq = C::ld1(C::col(cbase, ctr8, oq, 1));
+                        pickq = yq < yp + (int)((f >> 2) & 1u);
+                        C::st1(C::col(cbase, ctr8, pickq ? oq : op, 1), (pickq ? yq : yp) + 1);   // KAS:254-261
+                    }
+                    __syncwarp();
+                }
+                if (active) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + pos), "r"(oA), "r"(pickq ? oq : op), "r"(pickq ? op : oq), "r"(f) : "memory");
+            }
+            ra0 = rb0;
+            wstart = nstart;
+        }
+    } else if (KIND <= 1 && SINGLE) {
+        // ---- capacity 1 and P <= CTA: chunk k = topic k = records [k*w, (k+1)*w). The inner loop has NO bounds logic: the
+        //      number of chunks that can run before the next ring-stage hand-over is computed outside it. ---------------------
+        const uint32_t nchunks = Q / w, nstages = (Q + G - 1) >> LG;
+        const uint32_t w16 = w * RB, rmask16 = (uint32_t)NS * G * RB - 1u;
+        const bool act = tid < w;               // loop-invariant: every chunk is full (Q = T * w)
+        uint32_t roff = (tid * RB) & rmask16;   // ring byte offset of my record of the current chunk
+        uint32_t pos = tid, k = 0;
+#define KA_SINGLE_BODY(RC, RN)                                                                                                  \
+        {                                                                                                                       \
+            if (KIND == 0) {                                                                                                    \
+                KA_SLOT0_CORE(RC, act, pos)                                                                                     \
+                roff = (roff + w16) & rmask16;                                                                                  \
+                asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(RN.x), "=r"(RN.y), "=r"(RN.z), "=r"(RN.w) : "r"(ring_s + roff)); \
+                KA_SLOT0_DECIDE(act, pos)                                                                                       \
+            } else {                                                                                                            \
+                KA_SLOT1_CORE(RC, act, pos)                                                                                     \
+                roff = (roff + w16) & rmask16;                                                                                  \
+                asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(RN.x), "=r"(RN.y), "=r"(RN.z), "=r"(RN.w) : "r"(ring_s + roff)); \
+                KA_SLOT1_DECIDE(act, pos)                                                                                       \
+            }                                                                                                                   \
+            if (!(expf & 4)) { if (WARP1) __syncwarp(); else ka_named_bar_sync(1, NT); }  /* level barrier */                  \
+            pos += w;                                                                                                           \
+        }
+        // chunks fully inside the ring stages this thread has seen land (a stage = G records = cps chunks + rps records)
+        const uint32_t cps = G / w, rps = G - cps * w;
+        uint32_t lim_chunks = 0, lim_rem = 0;
+        for (uint32_t sdone = 0; sdone < landed; ++sdone) {   // stages observed by the prologue
+            lim_chunks += cps; lim_rem += rps;
+            if (lim_rem >= w) { lim_rem -= w; ++lim_chunks; }
+        }
+        while (k < nchunks) {
+            // running chunk k prefetches the record of chunk k+1: hand consumed stages back and wait for the next one(s)
+            while (landed < nstages && lim_chunks < k + 2) {
+                if (tid == 0)   // every record below (k+1)*w is in registers or done (the last prefetch precedes a barrier)
+                    while (((released + 1u) << LG) <= (k + 1) * w) { ka_mbar_arrive(&empty[released & (NS - 1)]); ++released; }
+                ka_mbar_wait(&full[landed & (NS - 1)], (landed / NS) & 1u);
+                ++landed;
+                lim_chunks += cps; lim_rem += rps;
+                if (lim_rem >= w) { lim_rem -= w; ++lim_chunks; }
+            }
+            // chunks k .. k+n-1 run without a hand-over (after the last stage landed: all of them; the final prefetch reads
+            // a stale slot and is ignored)
+            const uint32_t n = landed >= nstages ? nchunks - k : min(nchunks, lim_chunks - 1u) - k;
+            uint32_t i = 0;
+            for (; i + 4 <= n; i += 4) {
+                KA_SINGLE_BODY(ra0, rb0)
+                KA_SINGLE_BODY(rb0, ra0)
+                KA_SINGLE_BODY(ra0, rb0)
+                KA_SINGLE_BODY(rb0, ra0)
+            }
+            for (; i < n; ++i) {
+                KA_SINGLE_BODY(ra0, rb0)
+                ra0 = rb0;
+            }
+            k += n;
+        }
+#undef KA_SINGLE_BODY
+    } else if (KIND <= 1) {
+        // ---- general chunking (chunk table, or levels wider than the CTA): one body per chunk, unrolled by two ---------------
+#define KA_SLOT_BODY(RC, RN)                                                                                                    \
+        {                                                                                                                       \
+            const uint32_t pos = start + tid;                                                                                   \
+            const bool active = pos < end;                                                                                      \
+            const uint32_t nstart = end;                                                                                        \
+            if (KIND == 0) {                                                                                                    \
+                KA_SLOT0_CORE(RC, active, pos)                                                                                  \
+                /* next chunk: bounds, stage hand-over, record prefetch: independent of the loads in flight */                \
+                const uint32_t nend = next_end(end);                                                                            \
+                if (__builtin_expect(nend > limit, 0)) cross_to(end, nend);   /* rare: a new ring stage */                      \
+                read_rec(nstart + tid, RN, rb1);                                                                                \
+                KA_SLOT0_DECIDE(active, pos)                                                                                    \
+                end = nend;                                                                                                     \
+            } else {                                                                                                            \
+                KA_SLOT1_CORE(RC, active, pos)                                                                                  \
+                const uint32_t nend = next_end(end);                                                                            \
+                if (__builtin_expect(nend > limit, 0)) cross_to(end, nend);                                                     \
+                read_rec(nstart + tid, RN, rb1);                                                                                \
+                KA_SLOT1_DECIDE(active, pos)                                                                                    \
+                end = nend;                                                                                                     \
             }                                                                                                                   \
             /* level barrier: every counter bump of this chunk is visible before the next chunk reads */                       \
             if (WARP1) __syncwarp(); else ka_named_bar_sync(1, NT);                                                             \
-            start = nstart; end = nend;                                                                                         \
+            start = nstart;                                                                                                     \
         }
         while (true) {
-            KA_ORDER3_BODY(ra0, rb0)
+            KA_SLOT_BODY(ra0, rb0)
             if (start >= Q) break;
-            KA_ORDER3_BODY(rb0, ra0)
+            KA_SLOT_BODY(rb0, ra0)
             if (start >= Q) break;
         }
-#undef KA_ORDER3_BODY
+#undef KA_SLOT_BODY
     } else {
         while (start < Q) {
             const uint32_t pos = start + tid;
@@ -376,21 +531,21 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
 
     if (!GCTR) {
         if (NT == 32) __syncwarp(); else ka_named_bar_sync(1, NT);
-        for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += NT) ctr8[(i / CW) * KA_MAX_SLOTS + (i % CW)] = ctr[i];
+        for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += NT) ctr8[(i / CW) * KA_MAX_SLOTS + (KIND <= 1 ? KIND : (int)(i % CW))] = ctr[i];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Emit (rows of <= 3 replicas): ordered record -> broker ids + list length, one thread per schedule
+// Emit (rows of <= 3 replicas): ordered record -> broker ids + list length + the slot-2 counters, one thread per schedule
 // position, fully parallel; keeps the id lookups and the 4 B/replica output stream off the serial chain.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ka_emit3_kernel(const uint4* __restrict__ rec, const uint16_t* __restrict__ perm,
                                                        const int64_t* __restrict__ part_off, int T, int P,
                                                        const int32_t* __restrict__ broker_id, uint32_t Q, int S, int32_t* __restrict__ out,
-                                                       int32_t* __restrict__ out_len) {
+                                                       int32_t* __restrict__ out_len, int32_t* __restrict__ ctr8) {
     const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= Q) return;
-    const uint4 r = rec[pos];   // ordered by the leader-order kernel: {o0, o1, o2, f}
+    const uint4 r = rec[pos];   // ordered by the slot chains: {o0, o1, o2, f}, o_r = broker index << 2
     const int len = (int)(r.w & 3u);
     uint32_t row = pos;
     if (perm) {  // schedule position -> partition row: topic base + ordinal
@@ -408,8 +563,10 @@ __global__ void __launch_bounds__(256) ka_emit3_kernel(const uint4* __restrict__
         row = (uint32_t)g0 + perm[pos];
     }
     int32_t* o = out + (size_t)row * S;
-    o[0] = len > 0 ? __ldg(broker_id + (r.x >> 4)) : -1;
-    if (S > 1) o[1] = len > 1 ? __ldg(broker_id + (r.y >> 4)) : -1;
-    if (S > 2) o[2] = len > 2 ? __ldg(broker_id + (r.z >> 4)) : -1;
+    o[0] = len > 0 ? __ldg(broker_id + (r.x >> 2)) : -1;
+    if (S > 1) o[1] = len > 1 ? __ldg(broker_id + (r.y >> 2)) : -1;
+    if (S > 2) o[2] = len > 2 ? __ldg(broker_id + (r.z >> 2)) : -1;
     if (out_len) out_len[row] = len;
+    // counter[list[2]][2] += 1 (KAS:254-261): never compared by a row of <= 3 replicas, i.e. a plain commutative sum
+    if (len > 2) atomicAdd(ctr8 + (size_t)(r.z >> 2) * KA_MAX_SLOTS + 2, 1);
 }

@@ -501,14 +501,17 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
         const int pp = c0 + lane;
         const bool valid = pp < P;
         int pos = pp;
+        bool first = pp == 0;   // first record of its conflict level (capacity 1 / failed topic: the topic is one level)
         if (LEVELS && live) {
             const uint32_t vm = __ballot_sync(KA_FULL, valid);
             if (valid) {
                 const int lv = ls.lvl[pp];
                 const uint32_t m = __match_any_sync(vm, lv);
-                pos = (int)ls.lcur[lv] + __popc(m & lt);
+                const uint32_t cur = ls.lcur[lv];   // cursor of the level; bit 15 = the level has been opened (P < 32768)
+                pos = (int)(cur & 0x7FFFu) + __popc(m & lt);
+                first = (m & lt) == 0u && !(cur & 0x8000u);
                 __syncwarp(vm);
-                if ((m & lt) == 0u) ls.lcur[lv] = (uint16_t)(ls.lcur[lv] + __popc(m));
+                if ((m & lt) == 0u) ls.lcur[lv] = (uint16_t)(((cur & 0x7FFFu) + __popc(m)) | 0x8000u);
             }
             __syncwarp();
         }
@@ -522,16 +525,16 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                 // Brokers are stored in the order getNodeProcessingOrder (KAS:188-200, called at KAS:267 with the k remaining
                 // brokers) scans them for slot 0: ascending list position i sits at scan position (i + |hash| % k) % k.
                 const int s2 = (int)((rot >> 4) & 1u), s3 = (int)((rot >> 5) & 3u);
-                const uint32_t dummy = (uint32_t)N << 4;  // counter row N: "infinite" counters, pads rows shorter than 3
-                uint32_t a0 = dummy, a1 = dummy, a2 = dummy, f = (uint32_t)k;
+                const uint32_t dummy = (uint32_t)N << 2;  // broker N: "infinite" counters, pads rows shorter than 3
+                uint32_t a0 = dummy, a1 = dummy, a2 = dummy, f = (uint32_t)k | (first ? 0x80u : 0u);
                 if (k == 1) {
-                    a0 = ix[0] << 4;
+                    a0 = ix[0] << 2;
                 } else if (k == 2) {
-                    a0 = ix[s2] << 4;       // s2 == 1: the higher id is scanned first
-                    a1 = ix[1 - s2] << 4;
+                    a0 = ix[s2] << 2;       // s2 == 1: the higher id is scanned first
+                    a1 = ix[1 - s2] << 2;
                 } else if (k >= 3) {
                     const int i0 = (3 - s3) % 3, i1 = (4 - s3) % 3, i2 = (5 - s3) % 3;  // list position at scan position 0, 1, 2
-                    a0 = ix[i0] << 4; a1 = ix[i1] << 4; a2 = ix[i2] << 4;
+                    a0 = ix[i0] << 2; a1 = ix[i1] << 2; a2 = ix[i2] << 2;
                     // slot 1 scans the remaining pair in ascending id order rotated by s2; for scan positions p < q:
                     // q wins iff c_q < c_p + e_pq, e_pq = s2 when p has the lower id, 1 - s2 otherwise
                     const uint32_t e01 = (uint32_t)(i0 < i1 ? s2 : 1 - s2), e02 = (uint32_t)(i0 < i2 ? s2 : 1 - s2),

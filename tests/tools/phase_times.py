@@ -42,7 +42,8 @@ sub = cl.subset(0, n)
 po, pid, ro, cur = sub.ragged()
 _, _, exp, _ = ol.run(ol.OracleContext(), sub.topic_names, po, pid, ro, cur, sub.broker_id, sub.rack_name, -1, cl.RF)
 ok = np.array_equal(d_out.cpu().numpy()[:n].reshape(-1, cl.RF), exp)
-knobs = " ".join("%s=%s" % (k[9:], v) for k, v in sorted(os.environ.items()) if k.startswith("KA_ORDER_"))
-print("%s [%s] KA_ORDER_THREADS=%s A=%.3fms T=%.3fms B=%.3fms total=%.3fms  rate=%.3g/s  verified(first %d topics)=%s" % (
+knobs = " ".join("%s=%s" % (k[9:], v) for k, v in sorted(os.environ.items()) if k.startswith("KA_ORDER_") or k.startswith("KA_CHAIN") or k.startswith("KA_PIPE"))
+print("%s [%s] KA_ORDER_THREADS=%s A=%.3fms T=%.3fms B1=%.3fms B2+emit=%.3fms chains_wall=%.3fms total=%.3fms  rate=%.3g/s  verified(first %d topics)=%s" % (
     a.workload, knobs, os.environ.get("KA_ORDER_THREADS", "-"), avg["sticky_spread_ms"], avg["level_tables_ms"], avg["leader_order_ms"],
+    avg["slot1_emit_ms"], avg["chains_wall_ms"],
     avg["total_ms"], cl.replicas / (avg["total_ms"] * 1e-3), n, ok))

@@ -12,6 +12,10 @@ for i, n in enumerate(h):
         print("%-90s %s" % (n, v[i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+print("kernels:", [rows[i][1][:90] for i in starts[:-1]])
+rows = rows[starts[which]:starts[which + 1]]
 h = rows[1]; idx = {n: i for i, n in enumerate(h)}
 stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
 tot = 0

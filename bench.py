@@ -199,6 +199,8 @@ class Workload:
         self.d_out = torch.empty((cl.T, cl.P, S), dtype=torch.int32, device="cuda")
         self.d_len = torch.empty((cl.T, cl.P), dtype=torch.int32, device="cuda")
         self.ctr_buf = torch.zeros(cl.N * 8, dtype=torch.int32, device="cuda")
+        self.col_buf = [torch.zeros(cl.N, dtype=torch.int32, device="cuda") for _ in range(2)]
+        self.ring_group = dist.new_group() if world > 1 else None   # the ring's own communicator
         self.kab = kab
 
     def device_step(self):
@@ -208,11 +210,22 @@ class Workload:
                                  self.d_out.data_ptr(), stream=self.sptr, sync=False)
         else:
             from kafka_assigner_b200 import multi
-            multi.ring_solve(self.rank, self.world,
-                             lambda: s.stage_dense_device(cl.T, self.d_hash.data_ptr(), cl.P, cl.RF, self.d_cur.data_ptr(), -1, S, stream=self.sptr),
-                             lambda: s.order_device(self.d_len.data_ptr(), self.d_out.data_ptr(), stream=self.sptr, sync=False),
-                             lambda t: s.export_counters_device(t.data_ptr(), self.sptr),
-                             lambda t: s.import_counters_device(t.data_ptr(), self.sptr), self.ctr_buf, self.dist, final_broadcast=False)
+            sp, dl, do = self.sptr, self.d_len.data_ptr(), self.d_out.data_ptr()
+
+            def phases():  # after stage(): rows <= 3 -> two slot chains handed on separately; else one fused chain
+                if s.staged_slot_chains() == 2:
+                    return [(lambda r=r: s.order_slot_device(r, sp), lambda t, r=r: s.export_counter_slot_device(r, t.data_ptr(), sp),
+                             lambda t, r=r: s.import_counter_slot_device(r, t.data_ptr(), sp), self.col_buf[r]) for r in (0, 1)]
+                return [(lambda: s.order_device(dl, do, stream=sp, sync=False), lambda t: s.export_counters_device(t.data_ptr(), sp),
+                         lambda t: s.import_counters_device(t.data_ptr(), sp), self.ctr_buf)]
+
+            def finish():
+                if s.staged_slot_chains() == 2:
+                    s.emit_device(dl, do, stream=sp, sync=False)
+
+            multi.ring_solve_phases(self.rank, self.world,
+                                    lambda: s.stage_dense_device(cl.T, self.d_hash.data_ptr(), cl.P, cl.RF, self.d_cur.data_ptr(), -1, S, stream=sp),
+                                    phases, self.dist, finish=finish, final_broadcast=False, group=self.ring_group)
 
     def check_status(self, what):
         """Synchronise; the lowest failing topic of the WHOLE run wins on every rank (KAG:173 aborts at the first throw)."""
@@ -460,7 +473,7 @@ def main():
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_desc(args.workload, args.kind, cl) + ("; x%d topic blocks, one per GPU" % world if world > 1 else ""),
                        "l2": "256 MiB buffer written between timed iterations (L2 flush); fresh Context per step",
-                       "parallelism": "topic-sharded stage + ring hand-off of Context.counter for the leader-order chain" if world > 1 else "single GPU",
+                       "parallelism": "topic-sharded stage; per-slot leader-order chains handed rank to rank (counter[.][0], then counter[.][1])" if world > 1 else "single GPU",
                        "extra": extra},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -127,6 +127,21 @@ int32_t ka_solve_dense_device(ka_ctx* ctx, int32_t T, const int32_t* d_topic_has
 int32_t ka_stage_dense_device(ka_ctx* ctx, int32_t T, const int32_t* d_topic_hash, int32_t P, int32_t RF,
                               const int32_t* d_cur_broker, int32_t desired_rf, int32_t out_stride, void* stream);
 int32_t ka_order_device(ka_ctx* ctx, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st);
+/* Rows of <= 3 replicas are ordered by TWO independent chains: slot r reads and bumps only counter[.][r] (KAS:263-278 with
+ * replicaId = r), slot 1 needs the slot-0 winners but slot 0 never waits for slot 1, and counter[.][2] is write-only
+ * (a commutative sum added by the emit). A topic-sharded run therefore hands counter[.][0] to the next rank as soon as its
+ * slot-0 chain is done, then counter[.][1]:
+ *   ka_staged_slot_chains()   2 if the staged block is ordered by per-slot chains (all rows <= 3), else 0 (use ka_order_device)
+ *   ka_order_slot_device()    the slot-0 (slot = 0) or slot-1 (slot = 1) chain of the staged block; slot 1 after slot 0
+ *   ka_emit_device()          ordered records -> d_out_broker / d_out_len, adds counter[.][2]; ends the staged solve
+ *   ka_ctx_{export,import}_counter_slot_device()  one counter column, d_column = N int32 on the device
+ * ka_order_device == slot 0 (internal stream) overlapped with slot 1 + emit, sub-block by sub-block. */
+int32_t ka_staged_slot_chains(ka_ctx* ctx);
+int32_t ka_order_slot_device(ka_ctx* ctx, int32_t slot, void* stream);
+int32_t ka_emit_device(ka_ctx* ctx, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st);
+int32_t ka_ctx_export_counter_slot_device(ka_ctx* ctx, int32_t slot, int32_t* d_column, void* stream);
+int32_t ka_ctx_import_counter_slot_device(ka_ctx* ctx, int32_t slot, const int32_t* d_column, void* stream);
+
 /* Index of the staged block's first topic in the whole run: ka_status.topic_index of stage/order solves is reported
  * relative to the run (rank g of a topic-sharded job passes the number of topics owned by ranks < g), so that the ranks
  * can agree on the LOWEST failing topic of the run (KAG:173 aborts at the first throw). Default 0. */

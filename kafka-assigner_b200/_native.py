@@ -30,6 +30,11 @@ SYMBOLS = {
     "ka_stage_dense_device": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp]),
     "ka_order_device": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "ka_ctx_set_topic_base": (_i32, [_vp, _i32]),
+    "ka_staged_slot_chains": (_i32, [_vp]),
+    "ka_order_slot_device": (_i32, [_vp, _i32, _vp]),
+    "ka_emit_device": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "ka_ctx_export_counter_slot_device": (_i32, [_vp, _i32, _vp, _vp]),
+    "ka_ctx_import_counter_slot_device": (_i32, [_vp, _i32, _vp, _vp]),
     "ka_last_status": (_i32, [_vp, _vp]),
     "ka_ctx_counter_slots": (_i32, [_vp]),
     "ka_ctx_get_counters": (_i32, [_vp, _vp]),

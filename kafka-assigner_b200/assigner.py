@@ -215,6 +215,36 @@ class Solver:
             return None
         return st
 
+    def staged_slot_chains(self):
+        """2 when the staged block is ordered by per-slot chains (rows <= 3), else 0."""
+        return int(self._L.ka_staged_slot_chains(self._h))
+
+    def order_slot_device(self, slot, stream=0):
+        """Slot-0 / slot-1 leader-order chain of the staged block (reads and bumps only counter[.][slot])."""
+        rc = self._L.ka_order_slot_device(self._h, int(slot), ctypes.c_void_p(stream) if stream else None)
+        if rc:
+            raise KassignError(rc, "ka_order_slot_device")
+
+    def emit_device(self, d_out_len, d_out, stream=0, sync=True):
+        st = KaStatus()
+        rc = self._L.ka_emit_device(self._h, ctypes.c_void_p(d_out_len) if d_out_len else None, ctypes.c_void_p(d_out),
+                                    ctypes.c_void_p(stream) if stream else None, ctypes.byref(st) if sync else None)
+        if not sync:
+            if rc:
+                raise KassignError(rc, "ka_emit_device")
+            return None
+        return st
+
+    def export_counter_slot_device(self, slot, d_ptr, stream=0):
+        rc = self._L.ka_ctx_export_counter_slot_device(self._h, int(slot), ctypes.c_void_p(d_ptr), ctypes.c_void_p(stream) if stream else None)
+        if rc:
+            raise KassignError(rc)
+
+    def import_counter_slot_device(self, slot, d_ptr, stream=0):
+        rc = self._L.ka_ctx_import_counter_slot_device(self._h, int(slot), ctypes.c_void_p(d_ptr), ctypes.c_void_p(stream) if stream else None)
+        if rc:
+            raise KassignError(rc)
+
     def last_status(self):
         st = KaStatus()
         self._L.ka_last_status(self._h, ctypes.byref(st))

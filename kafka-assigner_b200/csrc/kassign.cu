@@ -94,6 +94,7 @@ struct ka_ctx {
     cudaStream_t sb1 = nullptr;             // slot-0 chain stream (the slot-1 chain + emit run on the caller's stream)
     cudaEvent_t ev_chain_in = nullptr, ev_b1[KA_MAX_CHAIN_EVENTS] = {}, ev_chain[KA_MAX_CHAIN_EVENTS][4] = {};
     int chain_ev_next = 0, chain_used = 0;
+    bool slot_timed[2] = {false, false};   // ka_order_slot_device recorded ev_chain[slot][0..1]
     cudaEvent_t ev_in = nullptr, ev_stage[8] = {};
     cudaEvent_t ev_pipe[8][5] = {};
     int last_stages = 1;
@@ -274,6 +275,7 @@ int reset_flags(ka_ctx* c, cudaStream_t s) {
     c->h_pin->spin_flag = -1;
     c->chain_ev_next = 0;
     c->chain_used = 0;
+    c->slot_timed[0] = c->slot_timed[1] = false;
     KA_CUDA(cudaMemsetAsync(c->d_flags.p, 0xFF, 2 * sizeof(int), s));
     return KA_OK;
 }
@@ -400,6 +402,56 @@ int chain_subblocks(const StageDesc& d, int blocks_in_solve) {
     return std::min(n, KA_MAX_CHAIN_BLOCKS);
 }
 
+struct SubBlock { int t0, t1; int64_t r0, rq; };
+
+SubBlock sub_block(const StageDesc& d, int j, int nsub) {
+    SubBlock b;
+    b.t0 = (int)((int64_t)d.T * j / nsub);
+    b.t1 = (int)((int64_t)d.T * (j + 1) / nsub);
+    // ragged blocks are never cut (nsub == 1): sub-block rows follow from the dense shape
+    b.r0 = d.d_part_off ? 0 : (int64_t)b.t0 * d.P;
+    b.rq = d.d_part_off ? d.Q : (int64_t)(b.t1 - b.t0) * d.P;
+    return b;
+}
+
+// One slot chain (rows <= 3) over sub-block j of a staged block.
+int enq_slot_chain(ka_ctx* c, cudaStream_t s, const StageDesc& d, int slot, int j, int nsub) {
+    const Plan& pl = d.pl;
+    const SubBlock b = sub_block(d, j, nsub);
+    if (b.rq <= 0 || c->N <= 0) return KA_OK;
+    KaOrderParams o{};
+    o.N = c->N;
+    o.S = d.S;
+    o.uniform_width = pl.a_levels ? 0u : (uint32_t)d.P;
+    o.chunk_end = pl.a_levels ? c->d_lvl_end.as<uint32_t>() + d.q0 : nullptr;
+    o.ctr8 = c->d_ctr8.as<int32_t>();
+    o.ring_log2 = pl.b_ring_log2;
+    if (const char* e = std::getenv("KA_EXP")) o.exp_flags = std::atoi(e);
+    const int32_t* loff = pl.a_levels ? c->d_loff.as<int32_t>() + d.topic_base + d.blk : nullptr;
+    o.Q = (uint32_t)b.rq;
+    o.rec = c->d_rec.as<unsigned char>() + (size_t)(d.q0 + b.r0) * pl.rec_bytes;
+    o.pos_base = (uint32_t)b.r0;
+    o.chunk_lo_ptr = loff ? loff + b.t0 : nullptr;
+    o.chunk_hi_ptr = loff ? loff + b.t1 : nullptr;
+    KA_CUDA((slot == 0 ? launch_order<0, 992>(s, o, pl) : launch_order<1, 992>(s, o, pl)));
+    c->launches++;
+    return KA_OK;
+}
+
+// Emit of sub-block j (rows <= 3): ordered records -> broker ids, list lengths, slot-2 counters.
+int enq_emit_block(ka_ctx* c, cudaStream_t s, const StageDesc& d, int j, int nsub, int32_t* d_out, int32_t* d_out_len) {
+    const Plan& pl = d.pl;
+    const SubBlock b = sub_block(d, j, nsub);
+    if (b.rq <= 0 || c->N <= 0) return KA_OK;
+    ka_emit3_kernel<<<(unsigned)((b.rq + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(c->d_rec.as<unsigned char>() + (size_t)(d.q0 + b.r0) * pl.rec_bytes),
+        pl.a_levels ? c->d_perm.as<uint16_t>() + d.q0 + b.r0 : nullptr, d.d_part_off, b.t1 - b.t0, d.P, c->d_broker_id.as<int32_t>(),
+        (uint32_t)b.rq, d.S, d_out + (size_t)b.r0 * d.S, d_out_len ? d_out_len + b.r0 : nullptr, c->d_ctr8.as<int32_t>());
+    KA_CUDA(cudaGetLastError());
+    c->launches++;
+    return KA_OK;
+}
+
 // The serial chains through Context.counter (KAS:202-239) for a staged block + the parallel emit. d_out/d_out_len: the
 // block's rows. Rows <= 3: slot-0 chain on c->sb1, slot-1 chain + emit on `s`; the caller has made c->sb1 wait for the
 // stage (c->ev_chain_in recorded after kernel A / the counter import). Everything is joined back into `s`.
@@ -432,32 +484,18 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
     const int nsub = chain_subblocks(d, blocks_in_solve);
     cudaStream_t s1 = c->sb1;
     for (int j = 0; j < nsub; ++j) {
-        const int t0 = (int)((int64_t)d.T * j / nsub), t1 = (int)((int64_t)d.T * (j + 1) / nsub);
-        // ragged blocks are never cut (nsub == 1): sub-block rows follow from the dense shape
-        const int64_t r0 = d.d_part_off ? 0 : (int64_t)t0 * d.P, rq = d.d_part_off ? d.Q : (int64_t)(t1 - t0) * d.P;
-        if (rq <= 0) continue;
-        o.Q = (uint32_t)rq;
-        o.rec = rec + (size_t)r0 * pl.rec_bytes;
-        o.pos_base = (uint32_t)r0;
-        o.chunk_lo_ptr = loff ? loff + t0 : nullptr;
-        o.chunk_hi_ptr = loff ? loff + t1 : nullptr;
         const int e = c->chain_ev_next++ % KA_MAX_CHAIN_EVENTS;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][0], s1));
-        KA_CUDA((launch_order<0, 992>(s1, o, pl)));                      // slot-0 chain
+        int rc = enq_slot_chain(c, s1, d, 0, j, nsub);                    // slot-0 chain
+        if (rc != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][1], s1));
         KA_CUDA(cudaEventRecord(c->ev_b1[e], s1));
         KA_CUDA(cudaStreamWaitEvent(s, c->ev_b1[e], 0));
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][2], s));
-        KA_CUDA((launch_order<1, 992>(s, o, pl)));                       // slot-1 chain
-        ka_emit3_kernel<<<(unsigned)((rq + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(o.rec),
-                                                                     pl.a_levels ? c->d_perm.as<uint16_t>() + d.q0 + r0 : nullptr, d.d_part_off,
-                                                                     t1 - t0, d.P, c->d_broker_id.as<int32_t>(), (uint32_t)rq, S,
-                                                                     d_out + (size_t)r0 * S, d_out_len ? d_out_len + r0 : nullptr,
-                                                                     c->d_ctr8.as<int32_t>());
-        KA_CUDA(cudaGetLastError());
+        if ((rc = enq_slot_chain(c, s, d, 1, j, nsub)) != KA_OK) return rc;   // slot-1 chain
+        if ((rc = enq_emit_block(c, s, d, j, nsub, d_out, d_out_len)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][3], s));
         c->chain_used = std::min(c->chain_used + 1, KA_MAX_CHAIN_EVENTS);
-        c->launches += 3;
     }
     return KA_OK;
 }
@@ -616,6 +654,9 @@ int finish_status(ka_ctx* c, cudaStream_t s, ka_status* st) {
                 c->last_ms[2] += b1;
                 c->last_ms[6] += b2;
             }
+        } else if (c->slot_timed[0] || c->slot_timed[1]) {  // per-slot entry points (topic-sharded runs)
+            if (c->slot_timed[0]) cudaEventElapsedTime(&c->last_ms[2], c->ev_chain[0][0], c->ev_chain[0][1]);
+            if (c->slot_timed[1]) cudaEventElapsedTime(&c->last_ms[6], c->ev_chain[1][0], c->ev_chain[1][1]);
         } else {
             c->last_ms[2] = c->last_ms[7];  // rows of 4..8: one fused chain
         }
@@ -963,6 +1004,68 @@ int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, vo
     c->pending_status = true;
     if (st) return finish_status(c, s, st);
     return KA_OK;
+}
+
+int32_t ka_staged_slot_chains(ka_ctx* c) {
+    if (!c || !c->staged || !c->staged_block) return 0;
+    return c->staged_block->d.pl.rec_kind == 3 ? 2 : 0;
+}
+
+int32_t ka_order_slot_device(ka_ctx* c, int32_t slot, void* stream) {
+    if (!c) return KA_ERR_NO_DEVICE;
+    if (cudaSetDevice(c->device) != cudaSuccess) return KA_ERR_CUDA;
+    if (!c->staged || !c->staged_block || c->staged_block->d.pl.rec_kind != 3 || slot < 0 || slot > 1) return KA_ERR_BAD_ARG;
+    const StageDesc& d = c->staged_block->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nsub = chain_subblocks(d, 1);
+    cudaEvent_t e0 = c->ev_chain[slot][0], e1 = c->ev_chain[slot][1];
+    if (c->timing) cudaEventRecord(e0, s);
+    for (int j = 0; j < nsub; ++j) {
+        int rc = enq_slot_chain(c, s, d, slot, j, nsub);
+        if (rc != KA_OK) return rc;
+    }
+    if (c->timing) cudaEventRecord(e1, s);
+    c->slot_timed[slot] = c->timing;
+    return KA_OK;
+}
+
+int32_t ka_emit_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, void* stream, ka_status* st) {
+    if (!c) return set_status(st, KA_ERR_NO_DEVICE);
+    if (cudaSetDevice(c->device) != cudaSuccess) return set_status(st, KA_ERR_CUDA);
+    if (!c->staged || !c->staged_block || c->staged_block->d.pl.rec_kind != 3 || !d_out_broker) return set_status(st, KA_ERR_BAD_ARG);
+    const StageDesc& d = c->staged_block->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (c->timing) cudaEventRecord(c->ev[3], s);
+    if ((rc = enq_emit_block(c, s, d, 0, 1, d_out_broker, d_out_len)) != KA_OK) return set_status(st, rc);
+    if (c->timing) cudaEventRecord(c->ev[4], s);
+    if ((rc = enq_flags_readback(c, s)) != KA_OK) return set_status(st, rc);
+    if (c->timing) { cudaEventRecord(c->ev[5], s); c->ev_valid = true; }
+    c->staged = false;
+    c->last_was_staged = true;
+    c->last_stream = s;
+    c->pending_status = true;
+    if (st) return finish_status(c, s, st);
+    return KA_OK;
+}
+
+static int copy_counter_column(ka_ctx* c, int slot, int32_t* d_col, const int32_t* d_src, cudaStream_t s) {
+    if (!c) return KA_ERR_NO_DEVICE;
+    if (slot < 0 || slot >= KA_MAX_SLOTS || (!d_col && !d_src)) return KA_ERR_BAD_ARG;
+    KA_CUDA(cudaSetDevice(c->device));
+    if (c->N <= 0) return KA_OK;
+    int32_t* col = c->d_ctr8.as<int32_t>() + slot;
+    if (d_col) KA_CUDA(cudaMemcpy2DAsync(d_col, 4, col, KA_MAX_SLOTS * 4, 4, (size_t)c->N, cudaMemcpyDeviceToDevice, s));
+    else KA_CUDA(cudaMemcpy2DAsync(col, KA_MAX_SLOTS * 4, d_src, 4, 4, (size_t)c->N, cudaMemcpyDeviceToDevice, s));
+    return KA_OK;
+}
+
+int32_t ka_ctx_export_counter_slot_device(ka_ctx* c, int32_t slot, int32_t* d_column, void* stream) {
+    return copy_counter_column(c, slot, d_column, nullptr, (cudaStream_t)stream);
+}
+
+int32_t ka_ctx_import_counter_slot_device(ka_ctx* c, int32_t slot, const int32_t* d_column, void* stream) {
+    return copy_counter_column(c, slot, nullptr, d_column, (cudaStream_t)stream);
 }
 
 int32_t ka_ctx_set_topic_base(ka_ctx* c, int32_t topic_base) {

@@ -41,35 +41,66 @@ def agree_on_failure(local_first_bad, dist, tensor_factory):
     return int(t[0])
 
 
-def ring_solve(rank, world, stage, order, export_counters, import_counters, ctr_buf, dist, final_broadcast=True, status=None,
-               tensor_factory=None):
-    """Run one topic-sharded solve.
+def _p2p(dist, op, tensor, peer, group):
+    """One send or recv as a batched P2P op (NCCL: enqueued on the current stream, no host block; gloo: completes here)."""
+    if hasattr(dist, "batch_isend_irecv") and hasattr(dist, "P2POp"):
+        fn = dist.isend if op == "send" else dist.irecv
+        for req in dist.batch_isend_irecv([dist.P2POp(fn, tensor, peer, group)]):
+            req.wait()
+    elif op == "send":
+        dist.send(tensor, dst=peer)
+    else:
+        dist.recv(tensor, src=peer)
 
-    stage():            context-free stage of this rank's block (enqueue only)
-    order():            leader-order stage of the staged block against the local Context
-    export_counters(t)/import_counters(t): copy the local Context counters to / from tensor t
-    ctr_buf:            a tensor [N*slots] int32 on this rank's device, identical shape on all ranks
-    dist:               torch.distributed (or a stand-in with send/recv/broadcast)
-    status():           optional; returns None or the GLOBAL index of this rank's first failing topic (synchronises the
-                        rank). When given, the ranks agree on the lowest failing topic of the run, every rank raises
-                        RunAborted and the final broadcast is skipped (counters are undefined after an error). Callers that
-                        keep the solve asynchronous pass None and call agree_on_failure() themselves after synchronising.
+
+def ring_solve_phases(rank, world, stage, phases, dist, finish=None, final_broadcast=True, final_sums=(), status=None,
+                      tensor_factory=None, group=None):
+    """Topic-sharded solve as a pipeline of serial chains handed from rank to rank.
+
+    stage():   context-free stage of this rank's block (enqueue only).
+    phases:    list (or a callable returning the list, evaluated after stage()) of (run, export, import_, buf): every phase is
+               ONE serial chain over all topics of the run. Rank g receives buf from g-1, imports it, runs its part of the
+               chain, exports and sends to g+1 — then moves on to the next phase, so chain p+1 of rank g overlaps chain p of
+               the ranks behind it. With the per-slot leader-order chains of libkassign (slot r touches only counter[.][r])
+               the critical path is  world x slot0 + slot1  instead of  world x (slot0 + slot1).
+    finish():  after the last phase (e.g. the parallel emit).
+    final_sums: (export_delta, add_total, buf) triples for state that is a commutative SUM over the ranks' blocks — the slot-2
+               counters of rows <= 3: one all-reduce, the only collective of the path (and it never feeds a decision).
+    status / tensor_factory: as in ring_solve.
     """
     stage()
-    if rank > 0:
-        dist.recv(ctr_buf, src=rank - 1)
-        import_counters(ctr_buf)
-    order()
-    if rank < world - 1:
-        export_counters(ctr_buf)
-        dist.send(ctr_buf, dst=rank + 1)
+    if callable(phases):
+        phases = phases()
+    for run, export, import_, buf in phases:
+        if rank > 0:
+            _p2p(dist, "recv", buf, rank - 1, group)
+            import_(buf)
+        run()
+        if rank < world - 1:
+            export(buf)
+            _p2p(dist, "send", buf, rank + 1, group)
+    if finish is not None:
+        finish()
     if status is not None:
         bad = agree_on_failure(status(), dist, tensor_factory)
         if bad != NO_FAILURE:
             raise RunAborted(bad)
     if final_broadcast and world > 1:
-        if rank == world - 1:
-            export_counters(ctr_buf)
-        dist.broadcast(ctr_buf, src=world - 1)
-        if rank != world - 1:
-            import_counters(ctr_buf)
+        for run, export, import_, buf in phases:
+            if rank == world - 1:
+                export(buf)
+            dist.broadcast(buf, src=world - 1, group=group)
+            if rank != world - 1:
+                import_(buf)
+        for export_delta, add_total, buf in final_sums:
+            export_delta(buf)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            add_total(buf)
+
+
+def ring_solve(rank, world, stage, order, export_counters, import_counters, ctr_buf, dist, final_broadcast=True, status=None,
+               tensor_factory=None):
+    """Single-chain form (the whole counter table travels with one leader-order stage per rank): used for rows of 4..8
+    replicas and by backends that cannot split the slots. See ring_solve_phases."""
+    return ring_solve_phases(rank, world, stage, [(order, export_counters, import_counters, ctr_buf)], dist,
+                             final_broadcast=final_broadcast, status=status, tensor_factory=tensor_factory)

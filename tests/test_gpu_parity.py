@@ -312,6 +312,56 @@ def test_stage_order_split_and_counter_ring_on_one_gpu(native_lib, oracle):
     assert np.array_equal(np.concatenate(outs), exp)
 
 
+def test_per_slot_ring_on_one_gpu(native_lib, oracle):
+    """The topic-sharded protocol of multi.ring_solve_phases with three contexts on one device: every block staged
+    independently, then the slot-0 chain block after block (handing on counter[.][0] only), then the slot-1 chain the same
+    way, then the emits; counter[.][2] is the sum over the blocks. Output and final Context == one run over all topics."""
+    import torch
+    from kafka_assigner_b200 import multi
+    for shape in (dict(T=90, P=40, RF=3, N=50, R=5), dict(T=64, P=16, RF=3, N=120, R=6)):   # capacity 3 (levels) / capacity 1
+        full = kab.synth.make_cluster(seed=47, kind="mixed", **shape)
+        octx = oracle.OracleContext()
+        exp, _, est = util.oracle_dense(oracle, full, octx)
+        assert est.code == 0
+        world, N = 3, full.N
+        solvers, blocks = [], []
+        for r in range(world):
+            t0, t1 = multi.shard_range(full.T, world, r)
+            cl = kab.synth.make_cluster(seed=47, kind="mixed", t_offset=t0, **dict(shape, T=t1 - t0))
+            s = kab.Solver(0)
+            s.set_brokers(cl.broker_id, cl.rack_index)
+            s.set_topic_base(t0)
+            blocks.append((cl, torch.from_numpy(cl.topic_hash).cuda(), torch.from_numpy(cl.cur).cuda(),
+                           torch.empty((cl.T, cl.P, 3), dtype=torch.int32, device="cuda"), torch.empty((cl.T, cl.P), dtype=torch.int32, device="cuda")))
+            solvers.append(s)
+        col = torch.zeros(N, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        for r in range(world):
+            cl, dh, dc, do, dl = blocks[r]
+            solvers[r].stage_dense_device(cl.T, dh.data_ptr(), cl.P, cl.RF, dc.data_ptr(), -1, 3)
+            assert solvers[r].staged_slot_chains() == 2
+        for slot in (0, 1):
+            for r in range(world):
+                if r > 0:
+                    solvers[r].import_counter_slot_device(slot, col.data_ptr())
+                solvers[r].order_slot_device(slot)
+                solvers[r].export_counter_slot_device(slot, col.data_ptr())
+        outs = []
+        for r in range(world):
+            cl, dh, dc, do, dl = blocks[r]
+            st = solvers[r].emit_device(dl.data_ptr(), do.data_ptr())
+            assert st.code == 0
+            outs.append(do.cpu().numpy().reshape(-1, 3))
+            assert (dl.cpu().numpy() == 3).all()
+        assert np.array_equal(np.concatenate(outs), exp), shape
+        ctrs = [s.counters() for s in solvers]
+        final = ctrs[-1].copy()
+        final[:, 2] = sum(c[:, 2] for c in ctrs)
+        for i, bid in enumerate(full.broker_id):
+            for slot in range(3):
+                assert final[i, slot] == octx.counter(int(bid), slot), (shape, int(bid), slot)
+
+
 # ---- less-travelled code paths ----------------------------------------------------------------------------------------
 def _random_case(rng, broker_ids, n_topics, max_rf, max_parts=40, rack_groups=None, desired=-1):
     racks = {}

@@ -138,3 +138,52 @@ def test_failed_topic_aborts_every_rank_with_the_global_index(tmp_path, oracle):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     t0, _ = multi.shard_range(13, 2, 1)
     assert int(np.load(tmp_path / "abort_0.npy")[0]) == t0 and int(np.load(tmp_path / "abort_1.npy")[0]) == t0
+
+
+PHASE_WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from kafka_assigner_b200 import multi
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+# two serial chains (each a running total that every rank extends in rank order) + one commutative sum
+state = {"a": 0, "b": 0, "c": 10 * (rank + 1), "log": []}
+bufs = [torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64)]
+def mk(name, step):
+    def run():
+        state[name] = state[name] * 3 + step + rank      # order-dependent: only the rank-ordered chain gives the right value
+        state["log"].append("run_" + name)
+    def export(t): t[0] = state[name]
+    def import_(t): state[name] = int(t[0])
+    return run, export, import_
+pa, pb = mk("a", 1), mk("b", 5)
+csum = torch.zeros(1, dtype=torch.int64)
+multi.ring_solve_phases(rank, world, lambda: state["log"].append("stage"),
+                        lambda: [(pa[0], pa[1], pa[2], bufs[0]), (pb[0], pb[1], pb[2], bufs[1])], dist,
+                        finish=lambda: state["log"].append("finish"),
+                        final_sums=[(lambda t: t.__setitem__(0, state["c"]), lambda t: state.__setitem__("c_total", int(t[0])), csum)],
+                        group=dist.new_group())
+np.save(os.path.join(%(out)r, "ph_%%d.npy" %% rank), np.array([state["a"], state["b"], state["c_total"]]))
+assert state["log"] == ["stage", "run_a", "run_b", "finish"], state["log"]
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_phase_pipeline_world3_gloo(tmp_path):
+    """multi.ring_solve_phases: two serial chains extended in rank order, final broadcast of both, one all-reduced sum."""
+    script = tmp_path / "worker.py"
+    script.write_text(PHASE_WORKER % {"root": ROOT, "out": str(tmp_path)})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    a = b = 0
+    for g in range(3):
+        a, b = a * 3 + 1 + g, b * 3 + 5 + g
+    for g in range(3):
+        got = np.load(tmp_path / ("ph_%d.npy" % g))
+        assert list(got) == [a, b, 10 + 20 + 30]

@@ -291,6 +291,28 @@ class Workload:
             tot += time.perf_counter() - t0
         return tot
 
+    def timed_e2e_json(self, n, flush):
+        """Same solve, but the result leaves the GPU as the reference's reassignment JSON (KAG:169-186) built on the device."""
+        torch, cl = self.torch, self.cl
+        S = self.S
+        cap = 64 + cl.T * cl.P * (50 + 12 * S + max(len(x) for x in cl.topic_names))
+        if not hasattr(self, "h_json"):
+            self.h_json = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self.names_slab = self.solver.marshal_names(cl.topic_names)   # flat name slab, like the hashes and the replica slab
+        tot, nbytes = 0.0, 0
+        for i in range(n):
+            self.solver.reset()
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            text, st = self.solver.solve_dense_json(cl.topic_names, self.h_hash.numpy(), self.h_cur.numpy(), -1, json_buf=self.h_json.numpy(), check=False,
+                                                    names_slab=self.names_slab)
+            tot += time.perf_counter() - t0
+            if st.code != 0:
+                raise SystemExit("e2e json solve failed: %d" % st.code)
+            nbytes = len(text)
+        return tot, nbytes
+
     def max_over_ranks(self, x):
         t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
         if self.world > 1:
@@ -319,7 +341,7 @@ class Workload:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # c3 = the largest BASELINE.json configuration quoted "on 1 B200"; every --gpus N weak-scales c3 blocks
@@ -354,7 +376,7 @@ def main():
     # ---- workload: rank r owns topics [r*T, (r+1)*T) of a world*T-topic run (weak scaling) ----------
     wl = Workload(args.workload, args.kind, rank, world, local, torch, kab, dist, stream)
     cl, S, solver = wl.cl, wl.S, wl.solver
-    phase = {"sticky_spread_ms": [], "level_tables_ms": [], "leader_order_ms": []}
+    phase = {"sticky_spread_ms": [], "level_tables_ms": [], "leader_order_ms": [], "slot1_emit_ms": []}
 
     # ---- device-resident timing ----------------------------------------------------------------------
     wl.timed_device(args.warmup, flush)
@@ -378,12 +400,22 @@ def main():
     h2d = (wl.h_hash.numel() + wl.h_cur.numel()) * 4
     d2h = (wl.h_out.numel() + wl.h_len.numel()) * 4
 
+    e2e_json = None
+    if world == 1:
+        nj = max(3, min(args.steps, 10))
+        wl.timed_e2e_json(2, flush)
+        js, jbytes = wl.timed_e2e_json(nj, flush)
+        e2e_json = {"value": wl.units_total * nj / js, "unit": UNIT, "ms_per_step": 1e3 * js / nj, "json_bytes_per_step": jbytes,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": jbytes,
+                    "note": "ka_solve_dense_json: rows stay on the device, the reassignment JSON text (KAG:169-186) is built there and "
+                            "streamed out per pipeline block; inputs are the flat slabs (hashes, replicas, names)"}
+
     # ---- roofline of the dominant kernel (CUDA events recorded around each phase by the library) ------
     peak, peak_src = load_peaks()
     avg = {k: float(np.mean(v)) for k, v in phase.items()}
-    dom = max(avg, key=avg.get)
-    kname = {"sticky_spread_ms": "ka_sticky_spread_kernel", "level_tables_ms": "ka_level_scan_kernel + ka_level_fill_kernel",
-             "leader_order_ms": "ka_order_levels_kernel (+ ka_emit3_kernel)"}[dom]
+    dom = max((k for k in avg if k != "level_tables_ms"), key=avg.get)
+    kname = {"sticky_spread_ms": "ka_sticky_spread_kernel", "leader_order_ms": "ka_order_levels_kernel<0,...> (slot-0 chain)",
+             "slot1_emit_ms": "ka_order_levels_kernel<1,...> (slot-1 chain) + ka_emit3_kernel"}[dom]
     algo_bytes = ALGO_BYTES_PER_UNIT * wl.units_rank
     achieved = algo_bytes / (avg[dom] * 1e-3) / 1e9
     traffic = None
@@ -397,8 +429,9 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": avg[dom], "phase_ms": avg,
                 "per_phase_frac": {k: (algo_bytes / (v * 1e-3) / 1e9) / peak for k, v in avg.items() if v > 0},
-                "note": "leader ordering is a serial dependency chain through Context.counter (KAS:202-239); its bound is "
-                        "chain latency, not HBM bandwidth — see DESIGN.md"}
+                "note": "leader ordering is a serial dependency chain per replica slot through Context.counter (KAS:202-239); phase_ms are "
+                        "sums over the pipelined sub-blocks (the slot-0 and slot-1 chains overlap in time); the bound is chain "
+                        "latency, not HBM bandwidth — see DESIGN.md"}
 
     # ---- verification + CPU baseline ------------------------------------------------------------------
     from oracle import oracle_lib as ol
@@ -423,7 +456,7 @@ def main():
         if world == 1 and wl.units_rank <= 12_000_000:
             levels = chain_depth(cl.broker_id, wl.h_out.numpy().reshape(-1, S))
             roofline["chain"] = {"dag_depth": levels, "mean_width": wl.units_rank / S / levels,
-                                 "ns_per_dag_level": avg["leader_order_ms"] * 1e6 / levels,
+                                 "ns_per_dag_level_slot0_chain": avg["leader_order_ms"] * 1e6 / levels,
                                  "note": "exact semantics force one read-decide-bump round trip through the counters per dependency "
                                          "level; the kernel schedules per-topic conflict levels (>= the DAG depth) with one barrier each"}
         if world == 1 and not args.no_cpu_baseline:
@@ -478,6 +511,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host wall clock around the blocking call, max over ranks"},
+            "e2e_json": e2e_json,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -108,6 +108,16 @@ int32_t ka_solve_dense(ka_ctx* ctx, int32_t T, const int32_t* topic_hash, int32_
                        const int32_t* cur_broker, int32_t desired_rf, int32_t out_stride,
                        int32_t* out_len, int32_t* out_broker, ka_status* st);
 
+/* Dense solve + the reference's JSON emitter (KAG:169-186) in one call: the rows never leave the device, only the TEXT
+ *   {"partitions":[{"partition":p,"replicas":[..],"topic":"name"},...],"version":1}
+ * crosses PCIe, streamed block by block while later topic blocks are still being ordered. names = the T topic names
+ * concatenated (UTF-8, none needing JSON escapes — else KA_ERR_BAD_ARG: use the host emitter), name_off[T+1] their offsets;
+ * json = host buffer of json_cap bytes (pinned for full PCIe speed; KA_ERR_LIMIT if too small: 64 + sum over rows of
+ * (50 + 12*out_stride + name length) always suffices); *json_bytes = length of the text (not NUL-terminated). */
+int32_t ka_solve_dense_json(ka_ctx* ctx, int32_t T, const int32_t* topic_hash, int32_t P, int32_t RF,
+                            const int32_t* cur_broker, int32_t desired_rf, const char* names, const int64_t* name_off,
+                            char* json, int64_t json_cap, int64_t* json_bytes, ka_status* st);
+
 /* Dense form on DEVICE buffers (d_* are device pointers on the ctx's device; d_out_len may be NULL),
  * enqueued on `stream` (a cudaStream_t, NULL = the legacy default stream) — inputs already resident in
  * HBM, outputs left in HBM. If st != NULL the call synchronises the stream and fills *st; with

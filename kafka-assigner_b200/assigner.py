@@ -164,6 +164,33 @@ class Solver:
             raise_for_status(st, topic_names)
         return out, out_len, st
 
+    @staticmethod
+    def marshal_names(topic_names):
+        """(concatenated UTF-8 bytes, offsets[T+1]) — the name slab ka_solve_dense_json takes."""
+        enc = [n.encode("utf-8") for n in topic_names]
+        name_off = np.zeros(len(enc) + 1, dtype=np.int64)
+        name_off[1:] = np.cumsum([len(e) for e in enc])
+        return np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8), name_off
+
+    def solve_dense_json(self, topic_names, topic_hash, cur, desired_rf=-1, json_buf=None, check=True, names_slab=None):
+        """Solve + emit the reassignment JSON on the device (KAG:169-186); returns (bytes-like view of the text, status).
+        json_buf: optional writable uint8 numpy array (pinned memory for full PCIe speed); names_slab: marshal_names() result."""
+        cur = np.ascontiguousarray(cur, dtype=np.int32)
+        T, P, RF = cur.shape
+        th = np.ascontiguousarray(topic_hash, dtype=np.int32)
+        names, name_off = names_slab if names_slab is not None else self.marshal_names(topic_names)
+        S = max(RF, desired_rf, 1)
+        cap = 64 + T * P * (50 + 12 * S) + int(P * name_off[-1])
+        if json_buf is None:
+            json_buf = np.empty(cap, dtype=np.uint8)
+        nbytes = ctypes.c_int64(0)
+        st = KaStatus()
+        self._L.ka_solve_dense_json(self._h, T, _ptr(th), P, RF, _ptr(cur), int(desired_rf), _ptr(names), _ptr(name_off),
+                                    _ptr(json_buf), int(json_buf.size), ctypes.byref(nbytes), ctypes.byref(st))
+        if check:
+            raise_for_status(st, topic_names)
+        return json_buf[:nbytes.value], st
+
     def solve_ragged(self, topic_hash, part_off, part_id, rep_off, cur_broker, desired_rf, out_stride, check=True,
                      topic_names=None):
         th = np.ascontiguousarray(topic_hash, dtype=np.int32)

@@ -4,6 +4,7 @@
 // the topic loop of KafkaAssignmentGenerator.java:172-184. No CPU fallback exists in this library.
 #include "kassign_stage.cuh"
 #include "kassign_order.cuh"
+#include "kassign_json.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -94,6 +95,12 @@ struct ka_ctx {
     cudaStream_t sb1 = nullptr;             // slot-0 chain stream (the slot-1 chain + emit run on the caller's stream)
     cudaEvent_t ev_chain_in = nullptr, ev_b1[KA_MAX_CHAIN_EVENTS] = {}, ev_chain[KA_MAX_CHAIN_EVENTS][4] = {};
     int chain_ev_next = 0, chain_used = 0;
+    // device-side JSON emission (ka_solve_dense_json)
+    cudaStream_t sj = nullptr;
+    cudaEvent_t ev_json_in[KA_MAX_CHAIN_EVENTS] = {}, ev_json_scan[KA_MAX_CHAIN_EVENTS] = {};
+    DevBuf d_json, d_names, d_name_off, d_json_rowlen, d_json_blocksum, d_json_state;
+    unsigned long long* h_frag = nullptr;  // pinned [KA_MAX_CHAIN_EVENTS][2]: {first byte, bytes} of every fragment
+    struct JsonJob* json_job = nullptr;    // non-null while run_dense serves ka_solve_dense_json
     bool slot_timed[2] = {false, false};   // ka_order_slot_device recorded ev_chain[slot][0..1]
     cudaEvent_t ev_in = nullptr, ev_stage[8] = {};
     cudaEvent_t ev_pipe[8][5] = {};
@@ -402,6 +409,52 @@ int chain_subblocks(const StageDesc& d, int blocks_in_solve) {
     return std::min(n, KA_MAX_CHAIN_BLOCKS);
 }
 
+}  // namespace
+struct JsonJob {
+    int32_t* d_out;        // the solve's rows (device)
+    int32_t* d_out_len;
+    int S;
+    int blocks = 0;
+};
+namespace {
+
+// KAG:169-186 for a finished range of rows (a chain sub-block): rows -> JSON text at the running offset of d_json, on c->sj.
+int enq_json_rows(ka_ctx* c, cudaStream_t s_done, int64_t row0, int64_t rows, int topic0, int P, bool first, bool last) {
+    JsonJob* jj = c->json_job;
+    const int k = jj->blocks;
+    if (k >= KA_MAX_CHAIN_EVENTS) return KA_ERR_LIMIT;
+    KA_CUDA(cudaEventRecord(c->ev_json_in[k], s_done));
+    KA_CUDA(cudaStreamWaitEvent(c->sj, c->ev_json_in[k], 0));
+    KaJsonParams p{};
+    p.Q = (uint32_t)rows;
+    p.row0 = (uint32_t)row0;
+    p.P = std::max(P, 1);
+    p.topic0 = topic0;
+    p.name_off = c->d_name_off.as<int64_t>();
+    p.names = c->d_names.as<char>();
+    p.out = jj->d_out + row0 * jj->S;
+    p.out_len = jj->d_out_len + row0;
+    p.S = jj->S;
+    p.rowlen = c->d_json_rowlen.as<uint32_t>() + row0;
+    p.blocksum = c->d_json_blocksum.as<uint32_t>() + (row0 / 256) + k;
+    p.total = c->d_json_state.as<unsigned long long>();
+    p.frag = c->d_json_state.as<unsigned long long>() + 2 + 2 * k;
+    p.json = c->d_json.as<char>();
+    p.first = first;
+    p.last = last;
+    const int nblocks = (int)((rows + 255) / 256);
+    if (nblocks > 0) ka_json_len_kernel<<<nblocks, 256, 0, c->sj>>>(p);
+    ka_json_scan_kernel<<<1, 1024, 0, c->sj>>>(p, nblocks);
+    KA_CUDA(allow_smem(ka_json_write_kernel, KA_JSON_SMEM_BYTES + 16));
+    ka_json_write_kernel<<<std::max(nblocks, 1), 256, KA_JSON_SMEM_BYTES + 16, c->sj>>>(p);
+    KA_CUDA(cudaGetLastError());
+    KA_CUDA(cudaMemcpyAsync(c->h_frag + 2 * k, p.frag, 16, cudaMemcpyDeviceToHost, c->sj));
+    KA_CUDA(cudaEventRecord(c->ev_json_scan[k], c->sj));
+    c->launches += 3;
+    jj->blocks = k + 1;
+    return KA_OK;
+}
+
 struct SubBlock { int t0, t1; int64_t r0, rq; };
 
 SubBlock sub_block(const StageDesc& d, int j, int nsub) {
@@ -479,6 +532,7 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
         o.out_len = d_out_len;
         KA_CUDA((pl.rec_kind == 4 ? launch_order<4, 480>(s, o, pl) : launch_order<8, 224>(s, o, pl)));
         c->launches++;
+        if (c->json_job) return enq_json_rows(c, s, d.q0, d.Q, d.topic_base, d.P, d.blk == 0, d.blk == blocks_in_solve - 1);
         return KA_OK;
     }
     const int nsub = chain_subblocks(d, blocks_in_solve);
@@ -495,6 +549,11 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
         if ((rc = enq_slot_chain(c, s, d, 1, j, nsub)) != KA_OK) return rc;   // slot-1 chain
         if ((rc = enq_emit_block(c, s, d, j, nsub, d_out, d_out_len)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][3], s));
+        if (c->json_job) {   // the sub-block's rows are final: their JSON text can be built and streamed out now
+            const SubBlock b = sub_block(d, j, nsub);
+            if ((rc = enq_json_rows(c, s, d.q0 + b.r0, b.rq, d.topic_base + b.t0, d.P, d.blk == 0 && j == 0,
+                                    d.blk == blocks_in_solve - 1 && j == nsub - 1)) != KA_OK) return rc;
+        }
         c->chain_used = std::min(c->chain_used + 1, KA_MAX_CHAIN_EVENTS);
     }
     return KA_OK;
@@ -570,6 +629,7 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
         if ((rc = chain_fork(c, s)) != KA_OK) return rc;
         if ((rc = enq_order_emit(c, s, d, d_out, d_out_len, 1)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev[4], s));
+
         if (h_out && Q > 0 && c->N > 0) {
             KA_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)Q * S * 4, cudaMemcpyDeviceToHost, s));
             if (h_out_len) KA_CUDA(cudaMemcpyAsync(h_out_len, d_out_len, (size_t)Q * 4, cudaMemcpyDeviceToHost, s));
@@ -596,6 +656,7 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][3], s_main));
             if ((rc = enq_order_emit(c, s_main, d, d_out + d.q0 * S, d_out_len ? d_out_len + d.q0 : nullptr, K)) != KA_OK) return rc;
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][4], s_main));
+
             if (h_out && d.Q > 0 && c->N > 0) {
                 KA_CUDA(cudaMemcpyAsync(h_out + d.q0 * S, d_out + d.q0 * S, (size_t)d.Q * S * 4, cudaMemcpyDeviceToHost, s_main));
                 if (h_out_len) KA_CUDA(cudaMemcpyAsync(h_out_len + d.q0, d_out_len + d.q0, (size_t)d.Q * 4, cudaMemcpyDeviceToHost, s_main));
@@ -729,6 +790,10 @@ ka_ctx* ka_ctx_create(int32_t device) {
     for (auto& e : c->ev) cudaEventCreate(&e);
     if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
     if (cudaStreamCreateWithFlags(&c->sb1, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    if (cudaStreamCreateWithFlags(&c->sj, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_frag), 2 * KA_MAX_CHAIN_EVENTS * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) { delete c; return nullptr; }
+    for (auto& e : c->ev_json_in) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : c->ev_json_scan) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_chain_in, cudaEventDisableTiming);
     for (auto& e : c->ev_b1) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& row : c->ev_chain)
@@ -751,6 +816,11 @@ void ka_ctx_destroy(ka_ctx* c) {
         if (e) cudaEventDestroy(e);
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
     if (c->sb1) { cudaStreamSynchronize(c->sb1); cudaStreamDestroy(c->sb1); }
+    if (c->sj) { cudaStreamSynchronize(c->sj); cudaStreamDestroy(c->sj); }
+    if (c->h_frag) cudaFreeHost(c->h_frag);
+    for (auto& e : c->ev_json_in) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_json_scan) if (e) cudaEventDestroy(e);
+    for (DevBuf* b : {&c->d_json, &c->d_names, &c->d_name_off, &c->d_json_rowlen, &c->d_json_blocksum, &c->d_json_state}) b->release();
     if (c->ev_chain_in) cudaEventDestroy(c->ev_chain_in);
     for (auto& e : c->ev_b1) if (e) cudaEventDestroy(e);
     for (auto& row : c->ev_chain)
@@ -981,6 +1051,7 @@ int32_t ka_stage_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     rc = enq_stage(c, s, d);
     c->ev_mark = nullptr;
     if (rc != KA_OK) return rc;
+    if (c->timing) cudaEventRecord(c->ev[3], s);   // end of the stage (the chains may wait for another rank after this)
     c->staged = true;
     return KA_OK;
 }
@@ -992,7 +1063,6 @@ int32_t ka_order_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, vo
     cudaStream_t s = (cudaStream_t)stream;
     const StageDesc& d = c->staged_block->d;
     int rc;
-    if (c->timing) cudaEventRecord(c->ev[3], s);
     if ((rc = chain_fork(c, s)) != KA_OK) return set_status(st, rc);
     if ((rc = enq_order_emit(c, s, d, d_out_broker, d_out_len, 1)) != KA_OK) return set_status(st, rc);
     if (c->timing) cudaEventRecord(c->ev[4], s);
@@ -1036,7 +1106,6 @@ int32_t ka_emit_device(ka_ctx* c, int32_t* d_out_len, int32_t* d_out_broker, voi
     const StageDesc& d = c->staged_block->d;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (c->timing) cudaEventRecord(c->ev[3], s);
     if ((rc = enq_emit_block(c, s, d, 0, 1, d_out_broker, d_out_len)) != KA_OK) return set_status(st, rc);
     if (c->timing) cudaEventRecord(c->ev[4], s);
     if ((rc = enq_flags_readback(c, s)) != KA_OK) return set_status(st, rc);
@@ -1100,6 +1169,68 @@ int32_t ka_solve_dense(ka_ctx* c, int32_t T, const int32_t* topic_hash, int32_t 
     c->pending_status = true;
     ka_status local;
     return finish_status(c, s, st ? st : &local);
+}
+
+int32_t ka_solve_dense_json(ka_ctx* c, int32_t T, const int32_t* topic_hash, int32_t P, int32_t RF, const int32_t* cur_broker,
+                            int32_t desired_rf, const char* names, const int64_t* name_off, char* json, int64_t json_cap,
+                            int64_t* json_bytes, ka_status* st) {
+    const int S = std::max(std::max(RF, desired_rf), 1);
+    if (json_bytes) *json_bytes = 0;
+    int rc = validate_dense(c, T, P, RF, desired_rf, S, st);
+    if (rc != KA_OK) return rc;
+    const int64_t Q = (int64_t)T * P, R = Q * RF;
+    if ((T > 0 && (!topic_hash || !names || !name_off)) || (R > 0 && !cur_broker) || !json || json_cap < KA_JSON_HEAD_LEN + KA_JSON_TAIL_LEN)
+        return set_status(st, KA_ERR_BAD_ARG);
+    const int64_t name_bytes = T > 0 ? name_off[T] : 0;
+    for (int64_t i = 0; i < name_bytes; ++i) {  // org.json quote() would escape these: such names take the host emitter
+        const unsigned char ch = (unsigned char)names[i];
+        if (ch < 0x20 || ch == '"' || ch == '\\' || ch == '/') return set_status(st, KA_ERR_BAD_ARG, -1, -1, (int)ch);
+    }
+    if (cudaSetDevice(c->device) != cudaSuccess) return set_status(st, KA_ERR_CUDA);
+    if (c->pending_status) finish_status(c, c->last_stream, nullptr);
+    cudaStream_t s = c->stream;
+    KA_CUDA(c->d_hash.reserve((size_t)std::max(T, 1) * 4));
+    KA_CUDA(c->d_cur.reserve((size_t)std::max<int64_t>(R, 1) * 4));
+    KA_CUDA(c->d_out.reserve((size_t)std::max<int64_t>(Q, 1) * S * 4));
+    KA_CUDA(c->d_out_len.reserve((size_t)std::max<int64_t>(Q, 1) * 4));
+    KA_CUDA(c->d_json.reserve((size_t)json_cap));
+    KA_CUDA(c->d_names.reserve((size_t)std::max<int64_t>(name_bytes, 1)));
+    KA_CUDA(c->d_name_off.reserve((size_t)(T + 1) * 8));
+    KA_CUDA(c->d_json_rowlen.reserve((size_t)std::max<int64_t>(Q, 1) * 4));
+    KA_CUDA(c->d_json_blocksum.reserve((size_t)(Q / 256 + 2 * KA_MAX_CHAIN_EVENTS) * 4));
+    KA_CUDA(c->d_json_state.reserve((2 + 2 * KA_MAX_CHAIN_EVENTS) * 8));
+    KA_CUDA(cudaMemsetAsync(c->d_json_state.p, 0, (2 + 2 * KA_MAX_CHAIN_EVENTS) * 8, c->sj));
+    if (name_bytes > 0) KA_CUDA(cudaMemcpyAsync(c->d_names.p, names, (size_t)name_bytes, cudaMemcpyHostToDevice, c->sj));
+    if (T > 0) KA_CUDA(cudaMemcpyAsync(c->d_name_off.p, name_off, (size_t)(T + 1) * 8, cudaMemcpyHostToDevice, c->sj));
+    JsonJob job{c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>(), S, 0};
+    c->json_job = &job;
+    c->last_part_id = nullptr;
+    c->last_part_off = nullptr;
+    c->staged = false;
+    c->last_was_staged = false;
+    rc = T > 0 && c->N > 0 ? run_dense(c, s, T, P, RF, desired_rf, S, topic_hash, cur_broker, c->d_hash.as<int32_t>(), c->d_cur.as<int32_t>(),
+                                      c->d_out.as<int32_t>(), c->d_out_len.as<int32_t>(), nullptr, nullptr, st)
+                            : KA_ERR_BAD_ARG;
+    c->json_job = nullptr;
+    if (rc != KA_OK) { if (st && st->code != rc) set_status(st, rc); cudaStreamSynchronize(c->sj); return rc; }
+    c->last_stream = s;
+    c->pending_status = true;
+    // every block is enqueued; stream the fragments out as their sizes become known (later blocks are still in the chains)
+    int64_t total = 0;
+    bool overflow = false;
+    for (int k = 0; k < job.blocks; ++k) {
+        KA_CUDA(cudaEventSynchronize(c->ev_json_scan[k]));
+        const int64_t base = (int64_t)c->h_frag[2 * k], size = (int64_t)c->h_frag[2 * k + 1];
+        if (base + size > json_cap) { overflow = true; break; }
+        if (size > 0) KA_CUDA(cudaMemcpyAsync(json + base, c->d_json.as<char>() + base, (size_t)size, cudaMemcpyDeviceToHost, c->sj));
+        total = base + size;
+    }
+    KA_CUDA(cudaStreamSynchronize(c->sj));
+    ka_status local;
+    rc = finish_status(c, s, st ? st : &local);
+    if (rc == KA_OK && overflow) return set_status(st, KA_ERR_LIMIT, -1, -1, (int)std::min<int64_t>(json_cap, INT_MAX));
+    if (json_bytes) *json_bytes = rc == KA_OK ? total : 0;
+    return rc;
 }
 
 int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t* part_off,

@@ -291,7 +291,10 @@ std::vector<kassign::TopicInput> gatherTopics(const Snapshot& sn, const std::vec
     for (const std::string& n : names) {
         auto it = sn.assignment.find(n);
         if (it == sn.assignment.end()) {
-            if (failIfMissing) throw std::runtime_error("java.lang.NullPointerException (topic " + n + " has no assignment; KTA:51)");
+            // ZkUtils.getPartitionAssignmentForTopics yields an EMPTY map for a topic without partition records, so
+            // generateAssignment sees zero partitions: "Topic X does not have a positive replication factor!" (KTA:65-66), or
+            // no rows at all with --desired_replication_factor > 0. The solver reproduces both from an empty Assignment.
+            if (failIfMissing) out.push_back({n, kassign::Assignment{}});
             continue;
         }
         out.push_back({n, it->second});

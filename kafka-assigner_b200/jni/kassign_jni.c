@@ -30,12 +30,20 @@ JNIEXPORT void  JNICALL Java_siftscience_kafka_tools_NativeAssigner_destroy(JNIE
 JNIEXPORT void JNICALL Java_siftscience_kafka_tools_NativeAssigner_setBrokers(JNIEnv* e, jclass c, jlong h, jintArray ids, jobjectArray racks) {
     jsize n = (*e)->GetArrayLength(e, ids);
     jint* id = (*e)->GetIntArrayElements(e, ids, 0);
-    const char** names = calloc(n, sizeof *names); jstring* js = calloc(n, sizeof *js); int32_t* idx = malloc(n * sizeof *idx);
-    for (jsize i = 0; i < n; i++) { js[i] = (*e)->GetObjectArrayElement(e, racks, i); names[i] = js[i] ? (*e)->GetStringUTFChars(e, js[i], 0) : NULL; }
-    ka_rack_indices(n, (const int32_t*)id, names, idx);                 /* KAS:81-94 string-keyed racks */
-    ka_ctx_set_brokers((ka_ctx*)(intptr_t)h, n, (const int32_t*)id, idx);
-    for (jsize i = 0; i < n; i++) if (js[i]) (*e)->ReleaseStringUTFChars(e, js[i], names[i]);
+    const char** names = calloc(n ? n : 1, sizeof *names); jstring* js = calloc(n ? n : 1, sizeof *js); int32_t* idx = malloc((n ? n : 1) * sizeof *idx);
+    int32_t rc = (names && js && idx) ? KA_OK : KA_ERR_BAD_ARG;
+    if (rc == KA_OK) {
+        for (jsize i = 0; i < n; i++) { js[i] = (*e)->GetObjectArrayElement(e, racks, i); names[i] = js[i] ? (*e)->GetStringUTFChars(e, js[i], 0) : NULL; }
+        rc = ka_rack_indices(n, (const int32_t*)id, names, idx);            /* KAS:81-94 string-keyed racks */
+        if (rc == KA_OK) rc = ka_ctx_set_brokers((ka_ctx*)(intptr_t)h, n, (const int32_t*)id, idx);
+        for (jsize i = 0; i < n; i++) if (js[i]) (*e)->ReleaseStringUTFChars(e, js[i], names[i]);
+    }
     free(names); free(js); free(idx); (*e)->ReleaseIntArrayElements(e, ids, id, JNI_ABORT);
+    if (rc != KA_OK) {   /* the Java side updates its cached broker table only when this call returns normally */
+        char msg[96];
+        snprintf(msg, sizeof msg, "kassign: broker table upload failed (code %d)", (int)rc);
+        (*e)->ThrowNew(e, (*e)->FindClass(e, "java/lang/RuntimeException"), msg);
+    }
 }
 
 JNIEXPORT void JNICALL Java_siftscience_kafka_tools_NativeAssigner_solve(JNIEnv* e, jclass c, jlong h, jobjectArray names, jintArray hash,

@@ -105,13 +105,29 @@ def test_print_reassignment_matches_oracle_json(cli, snapshot):
 
 
 @pytest.mark.gpu
+def test_topic_without_partition_records_behaves_like_an_empty_assignment(cli, snapshot):
+    """ZkUtils.getPartitionAssignmentForTopics gives an empty map for such a topic: KTA:65-66 throws unless
+    --desired_replication_factor is given, in which case the topic simply contributes no rows."""
+    rc, out, err = run(cli, "--zk_string", snapshot, "--mode", "PRINT_REASSIGNMENT", "--topics", "test,nosuch")
+    assert rc != 0 and "java.lang.IllegalStateException: Topic nosuch does not have a positive replication factor!" in err
+    assert "NEW ASSIGNMENT" not in out
+    rc, out, err = run(cli, "--zk_string", snapshot, "--mode", "PRINT_REASSIGNMENT", "--topics", "test,nosuch",
+                       "--desired_replication_factor", "2")
+    assert rc == 0, err
+    all_ids = [b["id"] for b in BROKERS]
+    racks = {b["id"]: b["rack"] for b in BROKERS if "rack" in b}
+    assert out.endswith("NEW ASSIGNMENT:\n" + expected_new_assignment(["test"], all_ids, racks, 2) + "\n")
+
+
+@pytest.mark.gpu
 def test_reassignment_errors_abort_without_new_assignment(cli, snapshot):
     rc, out, err = run(cli, "--zk_string", snapshot, "--mode", "PRINT_REASSIGNMENT", "--integer_broker_ids", "10,11")
     assert rc != 0
     assert "NEW ASSIGNMENT" not in out and out.startswith("CURRENT ASSIGNMENT:\n")      # KAG:160 printed, KAG:186 never
     assert "java.lang.IllegalStateException: Topic events has a higher replication factor (3) than available brokers!" in err
     rc, out, err = run(cli, "--zk_string", snapshot, "--mode", "PRINT_REASSIGNMENT", "--topics", "test,missing")
-    assert rc != 0 and "NullPointerException" in err and "NEW ASSIGNMENT" not in out   # KTA:51
+    # a topic without partition records is an EMPTY assignment (ZkUtils), i.e. KTA:65-66 — not the NPE of a null map
+    assert rc != 0 and "Topic missing does not have a positive replication factor!" in err and "NEW ASSIGNMENT" not in out
 
 
 @pytest.mark.gpu

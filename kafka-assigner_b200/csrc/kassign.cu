@@ -159,7 +159,7 @@ int park_counters(ka_ctx* c) {
 struct Plan {
     // kernel A
     int a_warps, a_load_bytes, a_slab_bytes, a_cnt_bytes, a_load_kind;  // kind 0=u8 1=u16 2=u32
-    int a_rackptr, a_rp_bytes;
+    int a_rackptr, a_rp_bytes, a_blob_bytes;
     int a_levels;                                   // 1: some topic may hold a broker twice -> conflict levels + tables
     int lv_owner_bytes, lv_last_bytes, lv_p_bytes;  // per-warp scratch of the level pass
     size_t a_smem;
@@ -197,7 +197,9 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, bool ragged
     pl.lv_p_bytes = pl.a_levels ? (int)align16((size_t)(std::max(Pmax, 1) + 2) * 2) : 0;
     const size_t per_warp = (size_t)pl.a_load_bytes + pl.a_slab_bytes + pl.a_cnt_bytes + 3 * (size_t)pl.a_rp_bytes +
                             pl.lv_owner_bytes + pl.lv_last_bytes + 2 * (size_t)pl.lv_p_bytes;
-    const size_t shared = 16 + (size_t)c->blob_bytes;
+    // the rack member lists (last part of the blob) are only read by the opt-in rack-pointer spread: not staged otherwise
+    pl.a_blob_bytes = pl.a_rackptr ? c->blob_bytes : c->roff_off * 2;
+    const size_t shared = 16 + (size_t)pl.a_blob_bytes;
     if (shared + per_warp > KA_SMEM_BUDGET) return set_status(st, KA_ERR_LIMIT, -1, -1, Pmax, N);
     pl.a_warps = (int)std::min<size_t>(16, (KA_SMEM_BUDGET - shared) / per_warp);
     pl.a_smem = shared + per_warp * pl.a_warps;
@@ -321,7 +323,7 @@ int enq_stage(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
         p.Pmax = d.Pmax;
         p.N = N;
         p.blob = c->d_blob.as<uint16_t>();
-        p.blob_bytes = c->blob_bytes;
+        p.blob_bytes = pl.a_blob_bytes;
         p.lut_off = c->lut_off;
         p.R = c->R;
         p.rackptr = pl.a_rackptr;

@@ -532,6 +532,32 @@ def test_pipelined_super_chunks_are_exact(native_lib, oracle):
     assert np.load("/tmp/_pl_bad.npy").tolist() == [est.code, est.topic_index, est.partition]
 
 
+def test_broker_tables_beyond_shared_memory(native_lib, oracle):
+    """N = 20 000 (counter columns still in shared memory) and N = 60 000 (global id->index LUT in kernel A,
+    counter columns in global memory for the chains — the GCTR path) must give the reference's answer, not KA_ERR_LIMIT."""
+    for N, R, T, P in ((20000, 50, 24, 300), (60000, 60, 6, 700)):
+        cl = kab.synth.make_cluster(T=T, P=P, RF=3, N=N, R=R, seed=0xB16 + N, kind="mixed")
+        exp, exp_len, est = oracle.fast_run_dense(oracle.FastContext(), cl.topic_hash, cl.cur, cl.broker_id, cl.rack_index)
+        assert est.code == 0
+        out, out_len, st = kab.Solver(0).solve_cluster(cl, check=False)
+        assert st.code == 0, (N, st.code, st.a, st.b)
+        assert np.array_equal(out.reshape(-1, 3), exp) and np.array_equal(out_len.reshape(-1), exp_len), N
+    # conflict levels (capacity 3) + chunk tables + window / general chunking, all with the counters forced into global memory
+    import subprocess, sys
+    code = ("import numpy as np, kafka_assigner_b200 as kab\n"
+            "from oracle import oracle_lib as ol\n"
+            "for T, P, N, R in ((40, 500, 600, 6), (200, 21, 40, 5), (12, 2500, 3000, 10)):\n"
+            "    cl = kab.synth.make_cluster(T=T, P=P, RF=3, N=N, R=R, seed=0xB17, kind='mixed')\n"
+            "    exp, ln, est = ol.fast_run_dense(ol.FastContext(), cl.topic_hash, cl.cur, cl.broker_id, cl.rack_index)\n"
+            "    out, out_len, st = kab.Solver(0).solve_cluster(cl, check=False)\n"
+            "    assert st.code == est.code == 0, (st.code, est.code)\n"
+            "    assert np.array_equal(out.reshape(-1, 3), exp), (T, P, N)\n"
+            "print('OK')\n")
+    env = dict(os.environ, KA_ORDER_GLOBAL_CTR="1", PYTHONPATH=util.os.path.dirname(util.HERE))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_large_capacity_load_counters_and_size_limit(native_lib, oracle):
     """cap = ceil(P*RF/N) > 255 switches kernel A's per-broker load counters to 16-bit; absurd sizes are refused."""
     cl = kab.synth.make_cluster(T=3, P=700, RF=2, N=4, R=2, seed=12, kind="random", n_old=4)   # cap = 350

@@ -418,16 +418,18 @@ def main():
              "slot1_emit_ms": "ka_order_levels_kernel<1,...> (slot-1 chain) + ka_emit3_kernel"}[dom]
     algo_bytes = ALGO_BYTES_PER_UNIT * wl.units_rank
     achieved = algo_bytes / (avg[dom] * 1e-3) / 1e9
-    traffic = None
+    traffic = None   # dram__bytes_read+write of the dominant kernel's launches of ONE step (ncu --cache-control none), like kernel_ms
     tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(kname.split(" ")[0])
+            per = json.load(open(tpath))["per_kernel_dram_bytes_per_step"]
+            sym = {"sticky_spread_ms": "ka_sticky_spread_kernel", "leader_order_ms": "ka_order_levels_kernel<0", "slot1_emit_ms": "ka_order_levels_kernel<1"}[dom]
+            traffic = sum(v for k, v in per.items() if k.startswith(sym)) or None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                "kernel_ms": avg[dom], "phase_ms": avg,
+                "kernel_ms": avg[dom], "launches_of_kernel_per_step": "sub-blocks of the pipelined solve; kernel_ms, traffic and algorithmic bytes are per STEP (sums over them)", "phase_ms": avg,
                 "per_phase_frac": {k: (algo_bytes / (v * 1e-3) / 1e9) / peak for k, v in avg.items() if v > 0},
                 "note": "leader ordering is a serial dependency chain per replica slot through Context.counter (KAS:202-239); phase_ms are "
                         "sums over the pipelined sub-blocks (the slot-0 and slot-1 chains overlap in time); the bound is chain "

@@ -1,7 +1,7 @@
 /* kassign_jni.c — JNI shim over include/kassign.h for NativeKafkaTopicAssigner.java.
  * NOT compiled in this repository: the build image has no jni.h. Build on a box with a JDK:
- *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude kafka-assigner_b200/jni/kassign_jni.c \
- *       -Lkafka-assigner_b200/csrc -lkassign -o libkassign_jni.so */
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude kafka_assigner_b200/jni/kassign_jni.c \
+ *       -Lkafka_assigner_b200/csrc -lkassign -o libkassign_jni.so */
 #include <jni.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -289,9 +289,9 @@ int reset_flags(ka_ctx* c, cudaStream_t s) {
     return KA_OK;
 }
 
-template <typename LoadT, bool LEVELS>
-cudaError_t launch_stage(ka_ctx* c, cudaStream_t s, const KaSolveParams& p, const Plan& pl, int T) {
-    auto kern = ka_sticky_spread_kernel<LoadT, LEVELS>;
+template <typename LoadT, bool LEVELS, int SM>
+cudaError_t launch_stage_t(ka_ctx* c, cudaStream_t s, const KaSolveParams& p, const Plan& pl, int T) {
+    auto kern = ka_sticky_spread_kernel<LoadT, LEVELS, SM>;
     const int threads = pl.a_warps * 32;
     cudaError_t e = allow_smem(kern, pl.a_smem);
     if (e != cudaSuccess) return e;
@@ -302,6 +302,11 @@ cudaError_t launch_stage(ka_ctx* c, cudaStream_t s, const KaSolveParams& p, cons
     grid = std::min(grid, std::max(1, occ) * c->sm_count);
     kern<<<grid, threads, pl.a_smem, s>>>(p, pl.a_load_bytes, pl.a_slab_bytes, pl.a_cnt_bytes, pl.lv_owner_bytes, pl.lv_last_bytes, pl.lv_p_bytes);
     return cudaGetLastError();
+}
+
+template <typename LoadT, bool LEVELS>
+cudaError_t launch_stage(ka_ctx* c, cudaStream_t s, const KaSolveParams& p, const Plan& pl, int T) {
+    return p.S <= 3 ? launch_stage_t<LoadT, LEVELS, 3>(c, s, p, pl, T) : launch_stage_t<LoadT, LEVELS, 8>(c, s, p, pl, T);
 }
 
 // Context-free part of a block (shards across GPUs): kernel A (records in schedule order) + the level tables.

@@ -79,7 +79,9 @@ struct KaLevelScratch {
     uint16_t* lcur;    // [P+2] per-level cursor of the stable counting sort
 };
 
-template <typename LoadT, bool LEVELS>
+// SM = compile-time bound on the row stride S (3 for every BASELINE config): sizes the per-partition rack lists of the spread
+// phase, so that RF = 3 runs 3-wide compares instead of 8-wide ones.
+template <typename LoadT, bool LEVELS, int SM>
 __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, LoadT* load, uint16_t* slab, uint8_t* cnt,
                                uint16_t* rpos, uint16_t* rst, uint16_t* rkk, const KaLevelScratch& ls) {
     const int lane = threadIdx.x & 31;
@@ -268,15 +270,15 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                     const int pp = c0 + src;
                     int rem = __shfl_sync(KA_FULL, need, src);
                     int k = (int)cnt[pp];
-                    uint32_t ur[KA_MAX_SLOTS];  // racks already holding this partition (warp-uniform)
+                    uint32_t ur[SM];  // racks already holding this partition (warp-uniform)
 #pragma unroll
-                    for (int i = 0; i < KA_MAX_SLOTS; ++i) ur[i] = i < k ? (uint32_t)tab.rack[slab[pp * S + i]] : 0xFFFFFFFFu;
+                    for (int i = 0; i < SM; ++i) ur[i] = i < k ? (uint32_t)tab.rack[slab[pp * S + i]] : 0xFFFFFFFFu;
                     while (rem > 0) {
                         uint32_t best = 0xFFFFFFFFu;
                         for (int r = lane; r < R; r += 32) {
                             bool used = false;
 #pragma unroll
-                            for (int i = 0; i < KA_MAX_SLOTS; ++i) used = used || (ur[i] == (uint32_t)r);
+                            for (int i = 0; i < SM; ++i) used = used || (ur[i] == (uint32_t)r);
                             const uint32_t cnd = used ? 0xFFFFFFFFu : (((uint32_t)rpos[r] << 16) | (uint32_t)r);
                             best = min(best, cnd);
                         }
@@ -292,7 +294,7 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                             slab[pp * S + k] = (uint16_t)idx;
                         }
 #pragma unroll
-                        for (int i = 0; i < KA_MAX_SLOTS; ++i)
+                        for (int i = 0; i < SM; ++i)
                             if (i == k) ur[i] = (uint32_t)r;
                         ++k;
                         --rem;
@@ -325,9 +327,9 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                 const int pp = c0 + src;
                 int rem = __shfl_sync(KA_FULL, need, src);
                 int k = (int)cnt[pp];
-                uint32_t ur[KA_MAX_SLOTS];  // racks already holding this partition (warp-uniform)
+                uint32_t ur[SM];  // racks already holding this partition (warp-uniform)
 #pragma unroll
-                for (int i = 0; i < KA_MAX_SLOTS; ++i) ur[i] = i < k ? (uint32_t)tab.rack[slab[pp * S + i]] : 0xFFFFFFFFu;
+                for (int i = 0; i < SM; ++i) ur[i] = i < k ? (uint32_t)tab.rack[slab[pp * S + i]] : 0xFFFFFFFFu;
                 bool adv = true;
                 for (int j = head; j < N && rem > 0; j += 32) {
                     const int pos = j + lane;
@@ -346,7 +348,7 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                     }
                     bool feas = nonfull;
 #pragma unroll
-                    for (int i = 0; i < KA_MAX_SLOTS; ++i) feas = feas && (ur[i] != rk);
+                    for (int i = 0; i < SM; ++i) feas = feas && (ur[i] != rk);
                     uint32_t fb = __ballot_sync(KA_FULL, feas);
                     while (fb && rem > 0) {
                         const int f = __ffs(fb) - 1;
@@ -357,7 +359,7 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                             slab[pp * S + k] = (uint16_t)cidx;
                         }
 #pragma unroll
-                        for (int i = 0; i < KA_MAX_SLOTS; ++i)
+                        for (int i = 0; i < SM; ++i)
                             if (i == k) ur[i] = crk;
                         ++k;
                         --rem;
@@ -518,9 +520,9 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
         if (valid) {
             const int k = live ? (int)cnt[pp] : 0;
             const uint16_t* row = slab + (size_t)pp * S;
-            uint32_t ix[KA_MAX_SLOTS];
+            uint32_t ix[SM];
 #pragma unroll
-            for (int i = 0; i < KA_MAX_SLOTS; ++i) ix[i] = (i < S && i < k) ? (uint32_t)row[i] : 0u;
+            for (int i = 0; i < SM; ++i) ix[i] = (i < S && i < k) ? (uint32_t)row[i] : 0u;
             if (p.rec_kind == 3) {
                 // Brokers are stored in the order getNodeProcessingOrder (KAS:188-200, called at KAS:267 with the k remaining
                 // brokers) scans them for slot 0: ascending list position i sits at scan position (i + |hash| % k) % k.
@@ -530,11 +532,12 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                 if (k == 1) {
                     a0 = ix[0] << 2;
                 } else if (k == 2) {
-                    a0 = ix[s2] << 2;       // s2 == 1: the higher id is scanned first
-                    a1 = ix[1 - s2] << 2;
+                    a0 = (s2 ? ix[1] : ix[0]) << 2;   // s2 == 1: the higher id is scanned first
+                    a1 = (s2 ? ix[0] : ix[1]) << 2;
                 } else if (k >= 3) {
                     const int i0 = (3 - s3) % 3, i1 = (4 - s3) % 3, i2 = (5 - s3) % 3;  // list position at scan position 0, 1, 2
-                    a0 = ix[i0] << 2; a1 = ix[i1] << 2; a2 = ix[i2] << 2;
+                    auto pick = [&](int i) { return i == 0 ? ix[0] : (i == 1 ? ix[1] : ix[2]); };   // no dynamic indexing (stays in registers)
+                    a0 = pick(i0) << 2; a1 = pick(i1) << 2; a2 = pick(i2) << 2;
                     // slot 1 scans the remaining pair in ascending id order rotated by s2; for scan positions p < q:
                     // q wins iff c_q < c_p + e_pq, e_pq = s2 when p has the lower id, 1 - s2 otherwise
                     const uint32_t e01 = (uint32_t)(i0 < i1 ? s2 : 1 - s2), e02 = (uint32_t)(i0 < i2 ? s2 : 1 - s2),
@@ -545,7 +548,8 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
                 if (LEVELS) p.perm[g0 + pos] = (uint16_t)pp;
             } else {
                 uint4* r8 = reinterpret_cast<uint4*>(p.rec) + 2 * (g0 + pos);
-                r8[0] = make_uint4(ix[0] | (ix[1] << 16), ix[2] | (ix[3] << 16), ix[4] | (ix[5] << 16), ix[6] | (ix[7] << 16));
+                r8[0] = make_uint4(ix[0] | (ix[1 % SM] << 16), ix[2 % SM] | (ix[3 % SM] << 16), ix[4 % SM] | (ix[5 % SM] << 16),
+                                   ix[6 % SM] | (ix[7 % SM] << 16));   // SM == 8 on this path (S > 3)
                 r8[1] = make_uint4((uint32_t)k | rot, (uint32_t)(g0 + pp), 0u, 0u);
             }
         }
@@ -557,7 +561,7 @@ __device__ void ka_solve_topic(const KaSolveParams& p, const KaTab& tab, int t, 
     __syncwarp();
 }
 
-template <typename LoadT, bool LEVELS>
+template <typename LoadT, bool LEVELS, int SM>
 __global__ void __launch_bounds__(512) ka_sticky_spread_kernel(const KaSolveParams p, int load_bytes, int slab_bytes, int cnt_bytes,
                                                                int lv_owner_bytes, int lv_last_bytes, int lv_p_bytes) {
     extern __shared__ __align__(16) unsigned char ka_smem[];
@@ -605,5 +609,5 @@ __global__ void __launch_bounds__(512) ka_sticky_spread_kernel(const KaSolvePara
 
     const int total_warps = gridDim.x * nwarp;
     for (int t = blockIdx.x * nwarp + warp; t < p.T; t += total_warps)
-        ka_solve_topic<LoadT, LEVELS>(p, tab, t, load, slab, cnt, rpos, rst, rkk, ls);
+        ka_solve_topic<LoadT, LEVELS, SM>(p, tab, t, load, slab, cnt, rpos, rst, rkk, ls);
 }

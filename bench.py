@@ -367,7 +367,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: kassign has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    json_fd = os.dup(1)
     if world > 1:
+        # NCCL writes its version banner to fd 1: park everything but the final JSON line on stderr (rank 0 prints ONE line)
+        sys.stdout.flush()
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -520,7 +524,8 @@ def main():
             "verified_vs_oracle": verified,
             "jvm_probe": jvm_probe(),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -400,6 +400,7 @@ def main():
         solver.reset()
         wl.e2e_step()
     e2e_s = wl.max_over_ranks(wl.timed_e2e(args.steps, flush))
+    e2e_stream_ms = solver.last_timing()["total_ms"]   # device-side span of the last e2e step (first copy in .. last copy out)
     e2e_val = wl.units_total * args.steps / e2e_s
     h2d = (wl.h_hash.numel() + wl.h_cur.numel()) * 4
     d2h = (wl.h_out.numel() + wl.h_len.numel()) * 4
@@ -516,7 +517,8 @@ def main():
                        "extra": extra},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host wall clock around the blocking call, max over ranks"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host wall clock around the blocking call, max over ranks",
+                    "stream_ms_last_step": e2e_stream_ms},
             "e2e_json": e2e_json,
             "gpu_launches": launches,
             "roofline": roofline,

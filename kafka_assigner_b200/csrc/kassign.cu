@@ -599,8 +599,13 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
     const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
     const int K = pipeline_stages(T, Q);
     StageDesc ds[8];
+    // Block boundaries: the first block's H2D and the last block's D2H are the only copies that nothing overlaps, so with
+    // host buffers the end blocks get half the weight of the inner ones (1:2:..:2:1).
+    const bool host_io = (h_cur != nullptr || h_out != nullptr) && K >= 3;
+    const int wsum = host_io ? 2 * (K - 1) : K;
+    auto bound = [&](int k) { return k <= 0 ? 0 : (k >= K ? T : (int)((int64_t)T * (host_io ? 2 * k - 1 : k) / wsum)); };
     for (int k = 0; k < K; ++k) {
-        const int t0 = (int)((int64_t)T * k / K), t1 = (int)((int64_t)T * (k + 1) / K);
+        const int t0 = bound(k), t1 = bound(k + 1);
         StageDesc& d = ds[k];
         d.topic_base = t0;
         d.T = t1 - t0;

@@ -19,4 +19,11 @@ except kab.IllegalStateException as e:
     print("expected:", e)
 big = kab.synth.make_cluster(T=40, P=16, RF=3, N=2000, R=20, seed=4, kind="random")   # global-LUT-free, larger table
 print(kab.Solver(0).solve_cluster(big)[2].code)
+lv = kab.synth.make_cluster(T=30, P=90, RF=3, N=60, R=6, seed=9, kind="mixed")      # capacity 5: conflict levels, chunk table, window mode
+print(kab.Solver(0).solve_cluster(lv)[2].code)
+wide = kab.synth.make_cluster(T=40, P=160, RF=3, N=600, R=6, seed=10, kind="mixed")  # capacity 1, 160-wide topics: bounds-free chain loop
+s = kab.Solver(0)
+s.set_brokers(wide.broker_id, wide.rack_index)
+text, st = s.solve_dense_json(wide.topic_names, wide.topic_hash, wide.cur)            # + the device-side JSON emitter
+print(st.code, len(text))
 print("sanitize cases done")

@@ -100,7 +100,12 @@ struct ka_ctx {
     cudaEvent_t ev_json_in[KA_MAX_CHAIN_EVENTS] = {}, ev_json_scan[KA_MAX_CHAIN_EVENTS] = {};
     DevBuf d_json, d_names, d_name_off, d_json_rowlen, d_json_blocksum, d_json_state;
     unsigned long long* h_frag = nullptr;  // pinned [KA_MAX_CHAIN_EVENTS][2]: {first byte, bytes} of every fragment
-    struct JsonJob* json_job = nullptr;    // non-null while run_dense serves ka_solve_dense_json
+    struct JsonJob* json_job = nullptr;
+    // host destination of a pipelined host-buffer solve: every chain sub-block is copied out on c->sj as soon as its emit is
+    // done, so that no D2H sits between two slot-1 chains on the caller's stream
+    int32_t* host_out = nullptr; int32_t* host_out_len = nullptr; int32_t* dev_out = nullptr; int32_t* dev_out_len = nullptr;
+    int out_copies = 0;
+    cudaEvent_t ev_out_done = nullptr;    // non-null while run_dense serves ka_solve_dense_json
     bool slot_timed[2] = {false, false};   // ka_order_slot_device recorded ev_chain[slot][0..1]
     cudaEvent_t ev_in = nullptr, ev_stage[8] = {};
     cudaEvent_t ev_pipe[8][5] = {};
@@ -556,6 +561,19 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
         if ((rc = enq_slot_chain(c, s, d, 1, j, nsub)) != KA_OK) return rc;   // slot-1 chain
         if ((rc = enq_emit_block(c, s, d, j, nsub, d_out, d_out_len)) != KA_OK) return rc;
         if (c->timing) KA_CUDA(cudaEventRecord(c->ev_chain[e][3], s));
+        if (c->host_out) {   // rows of this sub-block are final: copy them out on c->sj (on `s` itself once the events run out)
+            const SubBlock b = sub_block(d, j, nsub);
+            const int64_t r = d.q0 + b.r0;
+            cudaStream_t so = s;
+            if (c->out_copies < KA_MAX_CHAIN_EVENTS) {
+                KA_CUDA(cudaEventRecord(c->ev_json_in[c->out_copies], s));
+                KA_CUDA(cudaStreamWaitEvent(c->sj, c->ev_json_in[c->out_copies], 0));
+                c->out_copies++;
+                so = c->sj;
+            }
+            KA_CUDA(cudaMemcpyAsync(c->host_out + r * S, c->dev_out + r * S, (size_t)b.rq * S * 4, cudaMemcpyDeviceToHost, so));
+            if (c->host_out_len) KA_CUDA(cudaMemcpyAsync(c->host_out_len + r, c->dev_out_len + r, (size_t)b.rq * 4, cudaMemcpyDeviceToHost, so));
+        }
         if (c->json_job) {   // the sub-block's rows are final: their JSON text can be built and streamed out now
             const SubBlock b = sub_block(d, j, nsub);
             if ((rc = enq_json_rows(c, s, d.q0 + b.r0, b.rq, d.topic_base + b.t0, d.P, d.blk == 0 && j == 0,
@@ -598,6 +616,7 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
     const int rf_t = desired_rf >= 0 ? desired_rf : RF;
     const int64_t capmax = c->N > 0 ? ((int64_t)P * std::max(rf_t, 0) + c->N - 1) / c->N : 0;
     const int K = pipeline_stages(T, Q);
+    c->host_out = nullptr;
     StageDesc ds[8];
     // Block boundaries: the first block's H2D and the last block's D2H are the only copies that nothing overlaps, so with
     // host buffers the end blocks get half the weight of the inner ones (1:2:..:2:1).
@@ -648,7 +667,14 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
         }
     } else {
         cudaStream_t aux = c->aux;
+        const bool stream_out = h_out && ds[0].pl.rec_kind == 3 && !c->json_job;
+        c->host_out = stream_out ? h_out : nullptr;
+        c->host_out_len = stream_out ? h_out_len : nullptr;
+        c->dev_out = d_out;
+        c->dev_out_len = d_out_len;
+        c->out_copies = 0;
         KA_CUDA(cudaEventRecord(c->ev_in, s_main));           // inputs ready / earlier work on s_main done
+        if (stream_out) KA_CUDA(cudaStreamWaitEvent(c->sj, c->ev_in, 0));
         KA_CUDA(cudaStreamWaitEvent(aux, c->ev_in, 0));
         if ((rc = reset_flags(c, aux)) != KA_OK) return rc;
         for (int k = 0; k < K; ++k) {
@@ -669,11 +695,16 @@ int run_dense(ka_ctx* c, cudaStream_t s_main, int T, int P, int RF, int desired_
             if ((rc = enq_order_emit(c, s_main, d, d_out + d.q0 * S, d_out_len ? d_out_len + d.q0 : nullptr, K)) != KA_OK) return rc;
             if (c->timing) KA_CUDA(cudaEventRecord(c->ev_pipe[k][4], s_main));
 
-            if (h_out && d.Q > 0 && c->N > 0) {
+            if (h_out && d.Q > 0 && c->N > 0 && !c->host_out) {   // rows of 4..8: one copy per block on the caller's stream
                 KA_CUDA(cudaMemcpyAsync(h_out + d.q0 * S, d_out + d.q0 * S, (size_t)d.Q * S * 4, cudaMemcpyDeviceToHost, s_main));
                 if (h_out_len) KA_CUDA(cudaMemcpyAsync(h_out_len + d.q0, d_out_len + d.q0, (size_t)d.Q * 4, cudaMemcpyDeviceToHost, s_main));
             }
         }
+    }
+    if (c->host_out) {   // join the copy-out stream back into the caller's stream
+        KA_CUDA(cudaEventRecord(c->ev_out_done, c->sj));
+        KA_CUDA(cudaStreamWaitEvent(s_main, c->ev_out_done, 0));
+        c->host_out = nullptr;
     }
     if ((rc = enq_flags_readback(c, s_main)) != KA_OK) return rc;
     if (c->timing) { KA_CUDA(cudaEventRecord(c->ev[5], s_main)); c->ev_valid = true; }
@@ -807,6 +838,7 @@ ka_ctx* ka_ctx_create(int32_t device) {
     for (auto& e : c->ev_json_in) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& e : c->ev_json_scan) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_chain_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_out_done, cudaEventDisableTiming);
     for (auto& e : c->ev_b1) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& row : c->ev_chain)
         for (auto& e : row) cudaEventCreate(&e);
@@ -834,6 +866,7 @@ void ka_ctx_destroy(ka_ctx* c) {
     for (auto& e : c->ev_json_scan) if (e) cudaEventDestroy(e);
     for (DevBuf* b : {&c->d_json, &c->d_names, &c->d_name_off, &c->d_json_rowlen, &c->d_json_blocksum, &c->d_json_state}) b->release();
     if (c->ev_chain_in) cudaEventDestroy(c->ev_chain_in);
+    if (c->ev_out_done) cudaEventDestroy(c->ev_out_done);
     for (auto& e : c->ev_b1) if (e) cudaEventDestroy(e);
     for (auto& row : c->ev_chain)
         for (auto& e : row) if (e) cudaEventDestroy(e);
@@ -1036,6 +1069,7 @@ int32_t ka_stage_dense_device(ka_ctx* c, int32_t T, const int32_t* d_topic_hash,
     if (cudaSetDevice(c->device) != cudaSuccess) return KA_ERR_CUDA;
     if (c->pending_status) finish_status(c, c->last_stream, nullptr);
     cudaStream_t s = (cudaStream_t)stream;
+    c->host_out = nullptr;
     if (!c->staged_block) c->staged_block = new StagedBlock();
     StageDesc& d = c->staged_block->d;
     d = StageDesc();
@@ -1290,6 +1324,7 @@ int32_t ka_solve(ka_ctx* c, int32_t T, const int32_t* topic_hash, const int64_t*
     KA_CUDA(c->d_cur.reserve((size_t)std::max<int64_t>(R, 1) * 4));
     KA_CUDA(c->d_out.reserve((size_t)std::max<int64_t>(Q, 1) * S * 4));
     KA_CUDA(c->d_out_len.reserve((size_t)std::max<int64_t>(Q, 1) * 4));
+    c->host_out = nullptr;
     StageDesc d;
     d.T = T;
     d.Q = Q;

@@ -212,7 +212,7 @@ int make_plan(ka_ctx* c, int64_t Q, int S, int Pmax, int64_t capmax, bool ragged
     pl.rec_kind = S <= 3 ? 3 : (S == 4 ? 4 : 8);
     pl.rec_bytes = pl.rec_kind == 3 ? 16 : 32;
     const int cw = pl.rec_kind == 8 ? 8 : 4;
-    const int max_nt = pl.rec_kind == 3 ? 992 : (pl.rec_kind == 4 ? 480 : 224);  // + the producer warp <= 1024 / 512 / 256 threads
+    const int max_nt = pl.rec_kind == 3 ? 1024 : (pl.rec_kind == 4 ? 512 : 256);
     // rows <= 3: each slot chain keeps ONE counter column (+ the dummy broker that pads short rows) in shared memory
     const size_t ctr_bytes = pl.rec_kind == 3 ? (size_t)(std::max(N, 1) + 1) * 4 : (size_t)std::max(N, 1) * cw * 4;
     // record ring: KA_RING_STAGES stages of 2^lg records, as large as fits next to the counter table (<= 128 KB)
@@ -385,7 +385,7 @@ cudaError_t launch_order_t(cudaStream_t s, const KaOrderParams& o, const Plan& p
     auto kern = ka_order_levels_kernel<KIND, GCTR, MAXNT, SINGLE, WARP1>;
     cudaError_t e = allow_smem(kern, pl.b_smem);
     if (e != cudaSuccess) return e;
-    kern<<<1, pl.b_threads + 32, pl.b_smem, s>>>(o);
+    kern<<<1, pl.b_threads, pl.b_smem, s>>>(o);
     return cudaGetLastError();
 }
 
@@ -498,7 +498,7 @@ int enq_slot_chain(ka_ctx* c, cudaStream_t s, const StageDesc& d, int slot, int 
     o.pos_base = (uint32_t)b.r0;
     o.chunk_lo_ptr = loff ? loff + b.t0 : nullptr;
     o.chunk_hi_ptr = loff ? loff + b.t1 : nullptr;
-    KA_CUDA((slot == 0 ? launch_order<0, 992>(s, o, pl) : launch_order<1, 992>(s, o, pl)));
+    KA_CUDA((slot == 0 ? launch_order<0, 1024>(s, o, pl) : launch_order<1, 1024>(s, o, pl)));
     c->launches++;
     return KA_OK;
 }
@@ -542,7 +542,7 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
         o.chunk_hi_ptr = loff ? loff + d.T : nullptr;
         o.out = d_out;
         o.out_len = d_out_len;
-        KA_CUDA((pl.rec_kind == 4 ? launch_order<4, 480>(s, o, pl) : launch_order<8, 224>(s, o, pl)));
+        KA_CUDA((pl.rec_kind == 4 ? launch_order<4, 512>(s, o, pl) : launch_order<8, 256>(s, o, pl)));
         c->launches++;
         if (c->json_job) return enq_json_rows(c, s, d.q0, d.Q, d.topic_base, d.P, d.blk == 0, d.blk == blocks_in_solve - 1);
         return KA_OK;

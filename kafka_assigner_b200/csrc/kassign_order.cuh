@@ -7,8 +7,8 @@
 // walks the levels in order with ONE CTA: a level is processed by all threads in parallel (read the three counter rows,
 // take the KAS:226-234 decision, bump counter[list[r]][r]), levels are separated by one named barrier (or __syncwarp when
 // there is a single consumer warp). No tickets, no polling: cost per level = LDS + decision + STS + barrier.
-// The partition records arrive through a TMA ring (cp.async.bulk into shared memory, full/empty mbarriers per stage) fed by
-// a dedicated producer warp, so global latency never touches the chain.
+// The partition records arrive through a TMA ring (cp.async.bulk into shared memory, one mbarrier per stage, refilled by
+// thread 0 once per stage), so global latency never touches the chain.
 #pragma once
 #include "kassign_common.cuh"
 
@@ -161,14 +161,15 @@ __device__ __forceinline__ void ka_order_generic(const int (&c)[RS][RS], int len
 }
 
 // KIND 0 / 1 = slot-0 / slot-1 chain of rows <= 3 (16-byte records, rewritten in place), 4 = rows of 4, 8 = rows of 5..8
-// (32-byte records, all slots in one chain, rows written directly). blockDim = NT consumer threads + one producer warp.
-//   producer warp   streams the records into a ring of KA_RING_STAGES shared-memory stages with cp.async.bulk (TMA);
-//                   full[stage] mbarriers carry the byte count, empty[stage] mbarriers hand a consumed stage back
-//   consumers       chunk by chunk (<= NT records, never spanning two levels): thread i takes record i of the chunk,
-//                   loads its counter rows, decides, stores the bumps; one named barrier per chunk is the ONLY
+// (32-byte records, all slots in one chain, rows written directly). blockDim = NT threads.
+//   record ring     thread 0 streams the records into a ring of KA_RING_STAGES shared-memory stages with cp.async.bulk (TMA);
+//                   full[stage] mbarriers carry the byte count; a stage is refilled as soon as the level barrier shows that
+//                   every thread is done with it
+//   all threads     chunk by chunk (<= NT records, never spanning two levels): thread i takes record i of the chunk,
+//                   loads its counter rows, decides, stores the bumps; ONE `bar.sync 0` per chunk is the only
 //                   synchronisation on the chain. The next chunk's record is read from the ring before the barrier.
 template <int KIND, bool GCTR, int MAXNT, bool SINGLE, bool WARP1>
-__global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const KaOrderParams p) {
+__global__ void __launch_bounds__(MAXNT, 1) ka_order_levels_kernel(const KaOrderParams p) {
     constexpr int RS = KIND <= 1 ? 3 : KIND;                 // KIND 0 / 1: slot-0 / slot-1 chain of rows <= 3; 4 / 8: rows of 4 / 5..8
     constexpr int CW = KIND <= 1 ? 1 : (KIND == 4 ? 4 : 8);  // ints per broker in shared memory (one counter column for the slot chains)
     constexpr int RB = RS == 3 ? 16 : 32;                    // record bytes
@@ -178,13 +179,12 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     unsigned char* ring = ka_osmem;
     uint64_t* full = reinterpret_cast<uint64_t*>(ka_osmem + ((size_t)NS << p.ring_log2) * RB);
-    uint64_t* empty = full + NS;
-    volatile uint32_t* pin = reinterpret_cast<volatile uint32_t*>(empty + NS);   // 16 words
+    volatile uint32_t* pin = reinterpret_cast<volatile uint32_t*>(full + 2 * NS);   // 16 words
     int* ctr = reinterpret_cast<int*>(ka_osmem + ((size_t)NS << p.ring_log2) * RB + 256);
     // Loop invariants take a round trip through shared memory (volatile) so that they live in registers: ptxas otherwise
     // re-reads kernel parameters from the constant bank inside the chain loop, and every such load stalls a branch.
     if (tid == 0) {
-        pin[0] = p.Q; pin[1] = blockDim.x - 32; pin[2] = (uint32_t)p.ring_log2; pin[3] = p.uniform_width;
+        pin[0] = p.Q; pin[1] = blockDim.x; pin[2] = (uint32_t)p.ring_log2; pin[3] = p.uniform_width;
         pin[4] = (uint32_t)reinterpret_cast<uintptr_t>(p.rec); pin[5] = (uint32_t)(reinterpret_cast<uintptr_t>(p.rec) >> 32);
         pin[6] = (uint32_t)reinterpret_cast<uintptr_t>(p.ctr8); pin[7] = (uint32_t)(reinterpret_cast<uintptr_t>(p.ctr8) >> 32);
         pin[8] = (uint32_t)p.exp_flags;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
     const uint32_t G = 1u << LG;
 
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { ka_mbar_init(&full[i], 1); ka_mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NS; ++i) ka_mbar_init(&full[i], 1);
         ka_fence_mbar_init();
     }
     if (!GCTR)
@@ -213,21 +213,20 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
     ka_fence_proxy_async();   // generic-proxy writes above vs the async-proxy (TMA) writes that follow
     __syncthreads();
 
-    if (tid >= NT) {
-        // ---- producer warp: one elected lane keeps the ring full -------------------------------------------------------
-        if (lane == 0) {
-            const uint32_t nstages = (Q + G - 1) >> LG;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.rec);
-            for (uint32_t j = 0; j < nstages; ++j) {
-                const uint32_t slot = j & (NS - 1);
-                if (j >= (uint32_t)NS) ka_mbar_wait(&empty[slot], ((j / NS) - 1u) & 1u);  // consumers are done with stage j - NS
-                const uint32_t bytes = min(G, Q - (j << LG)) * RB;
-                ka_mbar_expect_tx(&full[slot], bytes);
-                ka_tma_bulk_g2s(ring + (size_t)slot * G * RB, src + (size_t)j * G * RB, bytes, &full[slot]);
-            }
-        }
-        return;
-    }
+    // ---- record ring: stage j of the stream lives in slot j % NS. Thread 0 issues the TMA copies: the first NS stages here,
+    //      stage j + NS as soon as every thread is done with stage j (the "hand-over", once per stage, off the per-level path).
+    //      No producer warp and no empty-barriers: the level barrier already tells thread 0 that a stage is consumed, and with
+    //      every thread of the CTA a consumer the level barrier is the plain `bar.sync 0` (measurably cheaper than a named
+    //      barrier with a register thread count — tests/tools/micro/level_floor.cu).
+    const uint32_t nstages_all = (Q + G - 1) >> LG;
+    auto issue_stage = [&](uint32_t j) {   // thread 0 only
+        const uint32_t slot = j & (NS - 1);
+        const uint32_t bytes = min(G, Q - (j << LG)) * RB;
+        ka_mbar_expect_tx(&full[slot], bytes);
+        ka_tma_bulk_g2s(ring + (size_t)slot * G * RB, reinterpret_cast<const unsigned char*>(p.rec) + (size_t)j * G * RB, bytes, &full[slot]);
+    };
+    if (tid == 0)
+        for (uint32_t j = 0; j < min(nstages_all, (uint32_t)NS); ++j) issue_stage(j);
 
     // ---- consumers ------------------------------------------------------------------------------------------------------
     const uint32_t rmask = (uint32_t)NS * G - 1u;
@@ -270,8 +269,13 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
     auto cross = [&](uint32_t held_end, uint32_t xlast) {
         // entering a new ring stage: hand finished stages back FIRST (every record below held_end is already in registers or
         // done), then wait for the stage(s) the next chunk needs
-        if (tid == 0)
-            while (((released + 1u) << LG) <= held_end) { ka_mbar_arrive(&empty[released & (NS - 1)]); ++released; }
+        if (tid == 0 && ((released + 1u) << LG) <= held_end) {
+            ka_fence_proxy_async();   // generic-proxy reads of the slot (all complete: a level barrier separates them) vs the TMA write
+            while (((released + 1u) << LG) <= held_end) {
+                if (released + NS < nstages_all) issue_stage(released + NS);
+                ++released;
+            }
+        }
         const uint32_t j = xlast >> LG;
         while (landed <= j) { ka_mbar_wait(&full[landed & (NS - 1)], (landed / NS) & 1u); ++landed; }
     };
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
                 asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(RN.x), "=r"(RN.y), "=r"(RN.z), "=r"(RN.w) : "r"(ring_s + roff)); \
                 KA_SLOT1_DECIDE(act, pos)                                                                                       \
             }                                                                                                                   \
-            if (!(expf & 4)) { if (WARP1) __syncwarp(); else ka_named_bar_sync(1, NT); }  /* level barrier */                  \
+            if (!(expf & 4)) { if (WARP1) __syncwarp(); else __syncthreads(); }  /* level barrier */                  \
             pos += w;                                                                                                           \
         }
         // chunks fully inside the ring stages this thread has seen land (a stage = G records = cps chunks + rps records)
@@ -412,8 +416,13 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
         while (k < nchunks) {
             // running chunk k prefetches the record of chunk k+1: hand consumed stages back and wait for the next one(s)
             while (landed < nstages && lim_chunks < k + 2) {
-                if (tid == 0)   // every record below (k+1)*w is in registers or done (the last prefetch precedes a barrier)
-                    while (((released + 1u) << LG) <= (k + 1) * w) { ka_mbar_arrive(&empty[released & (NS - 1)]); ++released; }
+                if (tid == 0 && ((released + 1u) << LG) <= (k + 1) * w) {   // every record below (k+1)*w is in registers or done
+                    ka_fence_proxy_async();
+                    while (((released + 1u) << LG) <= (k + 1) * w) {
+                        if (released + NS < nstages_all) issue_stage(released + NS);
+                        ++released;
+                    }
+                }
                 ka_mbar_wait(&full[landed & (NS - 1)], (landed / NS) & 1u);
                 ++landed;
                 lim_chunks += cps; lim_rem += rps;
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
                 end = nend;                                                                                                     \
             }                                                                                                                   \
             /* level barrier: every counter bump of this chunk is visible before the next chunk reads */                       \
-            if (WARP1) __syncwarp(); else ka_named_bar_sync(1, NT);                                                             \
+            if (WARP1) __syncwarp(); else __syncthreads();                                                             \
             start = nstart;                                                                                                     \
         }
         while (true) {
@@ -523,14 +532,14 @@ __global__ void __launch_bounds__(MAXNT + 32, 1) ka_order_levels_kernel(const Ka
                 }
             }
             if (active && p.out_len) p.out_len[orow] = len;
-            if (NT == 32) __syncwarp(); else ka_named_bar_sync(1, NT);
+            if (NT == 32) __syncwarp(); else __syncthreads();
             start = nstart; end = nend;
             ra0 = nb0; ra1 = nb1;
         }
     }
 
     if (!GCTR) {
-        if (NT == 32) __syncwarp(); else ka_named_bar_sync(1, NT);
+        if (NT == 32) __syncwarp(); else __syncthreads();
         for (uint32_t i = tid; i < (uint32_t)p.N * CW; i += NT) ctr8[(i / CW) * KA_MAX_SLOTS + (KIND <= 1 ? KIND : (int)(i % CW))] = ctr[i];
     }
 }

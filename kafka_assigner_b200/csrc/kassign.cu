@@ -380,32 +380,34 @@ int enq_stage(ka_ctx* c, cudaStream_t s, const StageDesc& d) {
     return KA_OK;
 }
 
-template <int KIND, int MAXNT, bool GCTR, bool SINGLE, bool WARP1>
+template <int KIND, int MAXNT, bool GCTR, bool SINGLE, bool WARP1, bool FULL>
 cudaError_t launch_order_t(cudaStream_t s, const KaOrderParams& o, const Plan& pl) {
-    auto kern = ka_order_levels_kernel<KIND, GCTR, MAXNT, SINGLE, WARP1>;
+    auto kern = ka_order_levels_kernel<KIND, GCTR, MAXNT, SINGLE, WARP1, FULL>;
     cudaError_t e = allow_smem(kern, pl.b_smem);
     if (e != cudaSuccess) return e;
     kern<<<1, pl.b_threads, pl.b_smem, s>>>(o);
     return cudaGetLastError();
 }
 
-// KIND 0 / 1: slot chains of rows <= 3 (chunk arithmetic and barrier flavour are compile-time); 4 / 8: rows of 4 / 5..8
+// KIND 0 / 1: slot chains of rows <= 3 (chunk arithmetic, barrier flavour, full chunks are compile-time); 4 / 8: rows of 4 / 5..8
 template <int KIND, int MAXNT>
 cudaError_t launch_order(cudaStream_t s, const KaOrderParams& o, const Plan& pl) {
     if constexpr (KIND > 1) {
-        return pl.b_gctr ? launch_order_t<KIND, MAXNT, true, false, false>(s, o, pl) : launch_order_t<KIND, MAXNT, false, false, false>(s, o, pl);
+        return pl.b_gctr ? launch_order_t<KIND, MAXNT, true, false, false, false>(s, o, pl) : launch_order_t<KIND, MAXNT, false, false, false, false>(s, o, pl);
     } else {
-        const bool single = o.uniform_width != 0 && o.uniform_width <= (uint32_t)pl.b_threads, warp1 = pl.b_threads == 32;
-        const int sel = (pl.b_gctr ? 4 : 0) | (single ? 2 : 0) | (warp1 ? 1 : 0);
+        const bool warp1 = pl.b_threads == 32;                                                          // window mode
+        const bool single = !warp1 && o.uniform_width != 0 && o.uniform_width <= (uint32_t)pl.b_threads;   // chunk = topic
+        const bool full = single && o.uniform_width == (uint32_t)pl.b_threads;                          // no idle lane
+        const int sel = (pl.b_gctr ? 4 : 0) | (warp1 ? 1 : (full ? 3 : (single ? 2 : 0)));
         switch (sel) {
-            case 0: return launch_order_t<KIND, MAXNT, false, false, false>(s, o, pl);
-            case 1: return launch_order_t<KIND, MAXNT, false, false, true>(s, o, pl);
-            case 2: return launch_order_t<KIND, MAXNT, false, true, false>(s, o, pl);
-            case 3: return launch_order_t<KIND, MAXNT, false, true, true>(s, o, pl);
-            case 4: return launch_order_t<KIND, MAXNT, true, false, false>(s, o, pl);
-            case 5: return launch_order_t<KIND, MAXNT, true, false, true>(s, o, pl);
-            case 6: return launch_order_t<KIND, MAXNT, true, true, false>(s, o, pl);
-            default: return launch_order_t<KIND, MAXNT, true, true, true>(s, o, pl);
+            case 0: return launch_order_t<KIND, MAXNT, false, false, false, false>(s, o, pl);
+            case 1: return launch_order_t<KIND, MAXNT, false, false, true, false>(s, o, pl);
+            case 2: return launch_order_t<KIND, MAXNT, false, true, false, false>(s, o, pl);
+            case 3: return launch_order_t<KIND, MAXNT, false, true, false, true>(s, o, pl);
+            case 4: return launch_order_t<KIND, MAXNT, true, false, false, false>(s, o, pl);
+            case 5: return launch_order_t<KIND, MAXNT, true, false, true, false>(s, o, pl);
+            case 6: return launch_order_t<KIND, MAXNT, true, true, false, false>(s, o, pl);
+            default: return launch_order_t<KIND, MAXNT, true, true, false, true>(s, o, pl);
         }
     }
 }
@@ -491,7 +493,6 @@ int enq_slot_chain(ka_ctx* c, cudaStream_t s, const StageDesc& d, int slot, int 
     o.chunk_end = pl.a_levels ? c->d_lvl_end.as<uint32_t>() + d.q0 : nullptr;
     o.ctr8 = c->d_ctr8.as<int32_t>();
     o.ring_log2 = pl.b_ring_log2;
-    if (const char* e = std::getenv("KA_EXP")) o.exp_flags = std::atoi(e);
     const int32_t* loff = pl.a_levels ? c->d_loff.as<int32_t>() + d.topic_base + d.blk : nullptr;
     o.Q = (uint32_t)b.rq;
     o.rec = c->d_rec.as<unsigned char>() + (size_t)(d.q0 + b.r0) * pl.rec_bytes;
@@ -532,7 +533,6 @@ int enq_order_emit(ka_ctx* c, cudaStream_t s, const StageDesc& d, int32_t* d_out
     o.ctr8 = c->d_ctr8.as<int32_t>();
     o.broker_id = c->d_broker_id.as<int32_t>();
     o.ring_log2 = pl.b_ring_log2;
-    if (const char* e = std::getenv("KA_EXP")) o.exp_flags = std::atoi(e);
     const int32_t* loff = pl.a_levels ? c->d_loff.as<int32_t>() + d.topic_base + d.blk : nullptr;
     unsigned char* rec = c->d_rec.as<unsigned char>() + (size_t)d.q0 * pl.rec_bytes;
     if (pl.rec_kind != 3) {  // rows of 4..8: one fused chain over all slots, rows written by the kernel

@@ -82,7 +82,6 @@ struct KaOrderParams {
     int32_t* out;
     int32_t* out_len;
     int ring_log2;              // log2(records per ring stage)
-    int exp_flags;              // timing experiments only (KA_EXP env): 1 = skip the global record store
 };
 
 #define KA_RING_STAGES 8
@@ -168,7 +167,7 @@ __device__ __forceinline__ void ka_order_generic(const int (&c)[RS][RS], int len
 //   all threads     chunk by chunk (<= NT records, never spanning two levels): thread i takes record i of the chunk,
 //                   loads its counter rows, decides, stores the bumps; ONE `bar.sync 0` per chunk is the only
 //                   synchronisation on the chain. The next chunk's record is read from the ring before the barrier.
-template <int KIND, bool GCTR, int MAXNT, bool SINGLE, bool WARP1>
+template <int KIND, bool GCTR, int MAXNT, bool SINGLE, bool WARP1, bool FULL>
 __global__ void __launch_bounds__(MAXNT, 1) ka_order_levels_kernel(const KaOrderParams p) {
     constexpr int RS = KIND <= 1 ? 3 : KIND;                 // KIND 0 / 1: slot-0 / slot-1 chain of rows <= 3; 4 / 8: rows of 4 / 5..8
     constexpr int CW = KIND <= 1 ? 1 : (KIND == 4 ? 4 : 8);  // ints per broker in shared memory (one counter column for the slot chains)
@@ -187,13 +186,11 @@ __global__ void __launch_bounds__(MAXNT, 1) ka_order_levels_kernel(const KaOrder
         pin[0] = p.Q; pin[1] = blockDim.x; pin[2] = (uint32_t)p.ring_log2; pin[3] = p.uniform_width;
         pin[4] = (uint32_t)reinterpret_cast<uintptr_t>(p.rec); pin[5] = (uint32_t)(reinterpret_cast<uintptr_t>(p.rec) >> 32);
         pin[6] = (uint32_t)reinterpret_cast<uintptr_t>(p.ctr8); pin[7] = (uint32_t)(reinterpret_cast<uintptr_t>(p.ctr8) >> 32);
-        pin[8] = (uint32_t)p.exp_flags;
     }
     __syncthreads();
     const uint32_t Q = pin[0], NT = pin[1];
     const int LG = (int)pin[2];
     const uint32_t w = pin[3];
-    const uint32_t expf = pin[8];
     uint4* const orec = reinterpret_cast<uint4*>((uintptr_t)pin[4] | ((uintptr_t)pin[5] << 32));
     int32_t* const ctr8 = reinterpret_cast<int32_t*>((uintptr_t)pin[6] | ((uintptr_t)pin[7] << 32));
     const uint32_t G = 1u << LG;
@@ -317,8 +314,8 @@ __global__ void __launch_bounds__(MAXNT, 1) ka_order_levels_kernel(const KaOrder
             const uint32_t op = is0 ? a1 : a0, oq = is2 ? a1 : a2;                                                              \
             const uint32_t esh = is2 ? f : (is1 ? f >> 1 : f >> 2);                                                             \
             if (ACTIVE) {                                                                                                       \
-                if (!(expf & 2)) C::st1(C::col(cbase, ctr8, oA, 0), vA + 1);   /* counter[list[0]][0] += 1 (KAS:254-261) */      \
-                if (!(expf & 1)) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + (POS)), "r"(op), "r"(oq), "r"((f & 0x83u) | (esh & 4u)), "r"(oA) : "memory"); \
+                C::st1(C::col(cbase, ctr8, oA, 0), vA + 1);   /* counter[list[0]][0] += 1 (KAS:254-261) */                       \
+                asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orec + (POS)), "r"(op), "r"(oq), "r"((f & 0x83u) | (esh & 4u)), "r"(oA) : "memory"); \
             }
 #define KA_SLOT1_CORE(RC, ACTIVE, POS)                                                                                          \
             const uint32_t op = RC.x, oq = RC.y, f = RC.z, oA = RC.w;                                                           \
@@ -387,7 +384,7 @@ __global__ void __launch_bounds__(MAXNT, 1) ka_order_levels_kernel(const KaOrder
         //      number of chunks that can run before the next ring-stage hand-over is computed outside it. ---------------------
         const uint32_t nchunks = Q / w, nstages = (Q + G - 1) >> LG;
         const uint32_t w16 = w * RB, rmask16 = (uint32_t)NS * G * RB - 1u;
-        const bool act = tid < w;               // loop-invariant: every chunk is full (Q = T * w)
+        const bool act = FULL || tid < w;       // loop-invariant: every chunk is full (Q = T * w); FULL: w == NT, no idle lane at all
         uint32_t roff = (tid * RB) & rmask16;   // ring byte offset of my record of the current chunk
         uint32_t pos = tid, k = 0;
 #define KA_SINGLE_BODY(RC, RN)                                                                                                  \
@@ -403,7 +400,7 @@ __global__ void __launch_bounds__(MAXNT, 1) ka_order_levels_kernel(const KaOrder
                 asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(RN.x), "=r"(RN.y), "=r"(RN.z), "=r"(RN.w) : "r"(ring_s + roff)); \
                 KA_SLOT1_DECIDE(act, pos)                                                                                       \
             }                                                                                                                   \
-            if (!(expf & 4)) { if (WARP1) __syncwarp(); else __syncthreads(); }  /* level barrier */                  \
+            if (WARP1) __syncwarp(); else __syncthreads();   /* level barrier */                                                \
             pos += w;                                                                                                           \
         }
         // chunks fully inside the ring stages this thread has seen land (a stage = G records = cps chunks + rps records)

@@ -5,8 +5,8 @@
 // of all topics; two partitions commute iff their broker sets are disjoint. Kernel A sorted every topic's partitions into
 // conflict levels (kassign_stage.cuh): the partitions of one level touch pairwise disjoint counter rows. This kernel
 // walks the levels in order with ONE CTA: a level is processed by all threads in parallel (read the three counter rows,
-// take the KAS:226-234 decision, bump counter[list[r]][r]), levels are separated by one named barrier (or __syncwarp when
-// there is a single consumer warp). No tickets, no polling: cost per level = LDS + decision + STS + barrier.
+// take the KAS:226-234 decision, bump counter[list[r]][r]), levels are separated by one `bar.sync 0` (or __syncwarp when
+// the CTA is a single warp). No tickets, no polling: cost per level = LDS + decision + STS + barrier.
 // The partition records arrive through a TMA ring (cp.async.bulk into shared memory, one mbarrier per stage, refilled by
 // thread 0 once per stage), so global latency never touches the chain.
 #pragma once
@@ -71,8 +71,9 @@ struct KaOrderParams {
     int N;
     int S;                      // output row stride (generic kinds write rows themselves)
     const void* rec;            // schedule-order records (16 B for rows <= 3, else 32 B), 16B aligned. Rows <= 3: each
-                                // record is overwritten in place by the ordered list {o0, o1, o2, f} (o_r = index << 4)
-    uint32_t uniform_width;     // > 0: level L = records [L*w, (L+1)*w), cut into chunks of blockDim-32;  0: chunk table
+                                // record is overwritten in place: {p, q, len|e, leader} by the slot-0 chain, the ordered list
+                                // {o0, o1, o2, f} (o_r = broker index << 2) by the slot-1 chain
+    uint32_t uniform_width;     // > 0: level L = records [L*w, (L+1)*w), cut into chunks of blockDim records;  0: chunk table
     const uint32_t* chunk_end;  // table mode: end position of each chunk of the STAGED block (a chunk never spans two levels)
     const int32_t* chunk_lo_ptr;  // device scalars: this launch walks chunks [*chunk_lo_ptr, *chunk_hi_ptr) of that table
     const int32_t* chunk_hi_ptr;  //   (loff[] of ka_level_scan_kernel at the first / one-past-last topic of the launch)

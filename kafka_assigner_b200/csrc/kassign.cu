@@ -1,4 +1,4 @@
-// kassign.cu — C ABI (include/kassign.h) over the sm_100a kernels in kassign_kernels.cuh.
+// kassign.cu — C ABI (include/kassign.h) over the sm_100a kernels in kassign_stage.cuh / kassign_order.cuh / kassign_json.cuh.
 //
 // Reference boundary: KafkaTopicAssigner.generateAssignment (KafkaTopicAssigner.java:42-72) batched over
 // the topic loop of KafkaAssignmentGenerator.java:172-184. No CPU fallback exists in this library.

@@ -13,7 +13,7 @@ import torch  # noqa: E402
 import kafka_assigner_b200 as kab  # noqa: E402
 from oracle import oracle_lib as ol  # noqa: E402
 
-print("| removed | live brokers | cap | A ms | tickets ms | B ms | total ms | assignments/s | oracle (1 core) assignments/s | verified |")
+print("| removed | live brokers | cap | A ms | chunk tables ms | slot-0 chain ms | total ms | assignments/s | oracle (1 core) assignments/s | verified |")
 print("|---|---|---|---|---|---|---|---|---|---|")
 for f in (0.01, 0.02, 0.05, 0.10, 0.20, 0.30, 0.40, 0.50):
     cl = kab.synth.make_config("c5", "mixed", remove_frac=f)

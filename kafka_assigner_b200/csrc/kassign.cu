@@ -454,6 +454,7 @@ int enq_json_rows(ka_ctx* c, cudaStream_t s_done, int64_t row0, int64_t rows, in
     p.total = c->d_json_state.as<unsigned long long>();
     p.frag = c->d_json_state.as<unsigned long long>() + 2 + 2 * k;
     p.json = c->d_json.as<char>();
+    p.cap = (unsigned long long)c->d_json.cap;
     p.first = first;
     p.last = last;
     const int nblocks = (int)((rows + 255) / 256);

@@ -26,6 +26,7 @@ struct KaJsonParams {
     unsigned long long* total;  // device scalar: bytes written so far (header included); advanced by this fragment
     unsigned long long* frag;   // [2] out: {first byte, byte count} of this fragment (the header / trailer included)
     char* json;
+    unsigned long long cap;     // bytes of `json`: a fragment that would end beyond it is measured but NOT written
     int first, last;            // write the header before / the trailer after this fragment
 };
 
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(1024) ka_json_scan_kernel(const KaJsonParams p
 __global__ void __launch_bounds__(256) ka_json_write_kernel(const KaJsonParams p) {
     extern __shared__ __align__(16) unsigned char ka_jsmem[];
     __shared__ uint32_t wsum[8];
+    if (p.frag[0] + p.frag[1] > p.cap) return;   // caller's buffer too small (uniform: the host reports KA_ERR_LIMIT)
     const uint32_t q = blockIdx.x * 256u + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = q < p.Q ? p.rowlen[q] : 0u;

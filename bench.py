@@ -462,10 +462,18 @@ def main():
         # the bound that actually applies to the leader-order kernel: barrier-separated levels
         if world == 1 and wl.units_rank <= 12_000_000:
             levels = chain_depth(cl.broker_id, wl.h_out.numpy().reshape(-1, S))
+            # measured floor of ONE barrier-separated shared-memory level (tests/tools/micro/level_floor.cu on this B200:
+            # 3 x LDS -> compare -> STS -> barrier): 120 cycles with one warp (__syncwarp), 135 with 4 warps, 190 with 8
+            warps = max(1, min(32, -(-min(cl.P, 1024) // 32))) if (cl.P * cl.RF <= cl.N) else 1
+            floor_cyc = {1: 120, 2: 125, 4: 135, 8: 190}.get(warps)
+            ns_level = avg["leader_order_ms"] * 1e6 / levels
             roofline["chain"] = {"dag_depth": levels, "mean_width": wl.units_rank / S / levels,
-                                 "ns_per_dag_level_slot0_chain": avg["leader_order_ms"] * 1e6 / levels,
+                                 "ns_per_dag_level_slot0_chain": ns_level,
+                                 "measured_floor_ns_per_level": (floor_cyc / 1.965) if floor_cyc else None,
+                                 "frac_of_latency_floor": ((floor_cyc / 1.965) / ns_level) if floor_cyc else None,
                                  "note": "exact semantics force one read-decide-bump round trip through the counters per dependency "
-                                         "level; the kernel schedules per-topic conflict levels (>= the DAG depth) with one barrier each"}
+                                         "level; the kernel schedules per-topic conflict levels (>= the DAG depth) with one barrier each; "
+                                         "floor = micro-benchmark of a bare level at this CTA size (null: not measured for it)"}
         if world == 1 and not args.no_cpu_baseline:
             sample = cpu_sample(cl, ol, 12.0)
             reps = 3 if sample.T == cl.T else 1

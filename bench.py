@@ -106,6 +106,17 @@ def cpu_sample(cl, ol, budget_s):
     return cl.subset(0, n) if n < cl.T else cl
 
 
+def config_desc(args, cl, world, extra):
+    """The `config` object of the JSON line — the same for both arms (the driver compares them), so every value says which arm
+    it is about; the bounded sample of the reference arm is in its `sample` / `cpu_baseline.sample` keys."""
+    return {"workload": workload_desc(args.workload, args.kind, cl) + ("; x%d topic blocks, one per GPU" % world if world > 1 else ""),
+            "l2": "GPU arm: 256 MiB buffer written between timed iterations (L2 flush); both arms: fresh Context per step",
+            "parallelism": ("GPU arm: topic-sharded stage, per-slot leader-order chains handed rank to rank (counter[.][0], then "
+                            "counter[.][1]); reference arm: rank 0, one host thread, one topic block") if world > 1
+                           else "GPU arm: single GPU; reference arm: one host thread",
+            "extra": extra}
+
+
 def run_reference(args):
     """Reference arm: the reference's algorithm (oracle port; no JVM exists in this image) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -128,7 +139,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": workload_desc(args.workload, args.kind, cl), "sample": "first %d of %d topics per step" % (sample.T, cl.T)},
+        "config": config_desc(args, cl, args.gpus, None),
+        "sample": "first %d of %d topics per step" % (sample.T, cl.T),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "first %d of %d topics (%d assignments) per step; single thread like the reference "
                                    "(KafkaAssignmentGenerator.java:173); host has %d cores" % (sample.T, cl.T, sample.replicas, os.cpu_count())},
@@ -519,10 +531,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_desc(args.workload, args.kind, cl) + ("; x%d topic blocks, one per GPU" % world if world > 1 else ""),
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush); fresh Context per step",
-                       "parallelism": "topic-sharded stage; per-slot leader-order chains handed rank to rank (counter[.][0], then counter[.][1])" if world > 1 else "single GPU",
-                       "extra": extra},
+            "config": config_desc(args, cl, world, extra),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host wall clock around the blocking call, max over ranks",
